@@ -1,0 +1,92 @@
+// C-ABI glue: error state, launch accounting, host-side weight packing, engine dispatch.
+#include "conv_common.cuh"
+#include <vector>
+
+namespace ctb {
+thread_local char g_err[512] = {0};
+thread_local int64_t g_launches = 0;
+
+static inline uint16_t f32_to_bf16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
+  const uint32_t lsb = (u >> 16) & 1u;
+  u += 0x7fffu + lsb;
+  return (uint16_t)(u >> 16);
+}
+}  // namespace ctb
+
+using namespace ctb;
+
+extern "C" const char* ct_last_error(void) { return g_err; }
+extern "C" int ct_abi_version(void) { return CTB200_ABI_VERSION; }
+extern "C" int64_t ct_launch_count(void) { return g_launches; }
+extern "C" void ct_reset_launch_count(void) { g_launches = 0; }
+
+static inline int tc_k_slices(int C_in, int KH, int KW) { return (KH * KW * C_in + 63) / 64; }
+
+extern "C" int64_t ct_packed_weight_bytes(int32_t engine, int32_t C_out, int32_t C_in, int32_t KH,
+                                          int32_t KW, int32_t n_tile) {
+  if (engine == CT_ENGINE_SIMT) {
+    const int64_t ldw = (C_out + 63) / 64 * 64;
+    return (int64_t)KH * KW * C_in * ldw * 4;
+  }
+  if (n_tile <= 0 || n_tile % 16 != 0 || n_tile > 256) return -1;
+  const int64_t n_tiles = (C_out + n_tile - 1) / n_tile;
+  return n_tiles * tc_k_slices(C_in, KH, KW) * (int64_t)n_tile * 64 * 2;
+}
+
+extern "C" int ct_pack_weights(int32_t engine, const float* w, int32_t C_out, int32_t C_in, int32_t KH,
+                               int32_t KW, int32_t n_tile, void* dst) {
+  CT_REQUIRE(w && dst, "null pointer");
+  CT_REQUIRE(C_out > 0 && C_in > 0 && KH > 0 && KW > 0, "bad shape");
+  const int taps = KH * KW;
+  if (engine == CT_ENGINE_SIMT) {
+    const int ldw = (C_out + 63) / 64 * 64;
+    float* o = (float*)dst;
+    memset(o, 0, (size_t)taps * C_in * ldw * 4);
+    for (int oc = 0; oc < C_out; ++oc)
+      for (int c = 0; c < C_in; ++c)
+        for (int t = 0; t < taps; ++t)
+          o[((size_t)t * C_in + c) * ldw + oc] = w[((size_t)oc * C_in + c) * taps + t];
+    return CT_OK;
+  }
+  CT_REQUIRE(n_tile > 0 && n_tile % 16 == 0 && n_tile <= 256, "bad n_tile");
+  CT_REQUIRE(C_in % 8 == 0, "C_in must be a multiple of 8 for the tcgen05 engine");
+  const int ks = tc_k_slices(C_in, KH, KW);
+  const int n_tiles = (C_out + n_tile - 1) / n_tile;
+  uint16_t* o = (uint16_t*)dst;
+  memset(o, 0, (size_t)n_tiles * ks * n_tile * 64 * 2);
+  for (int oc = 0; oc < C_out; ++oc) {
+    const int nt = oc / n_tile, r = oc % n_tile;
+    for (int t = 0; t < taps; ++t)
+      for (int c = 0; c < C_in; ++c) {
+        const int k = t * C_in + c;
+        const int s = k / 64, j = k % 64;
+        const int chunk = (j / 8) ^ (r & 7);           // 128B swizzle: 16B chunk index XOR row%8
+        const size_t off = ((size_t)nt * ks + s) * n_tile * 64 + (size_t)r * 64 + chunk * 8 + (j % 8);
+        o[off] = f32_to_bf16_rn(w[((size_t)oc * C_in + c) * taps + t]);
+      }
+  }
+  return CT_OK;
+}
+
+extern "C" int ct_conv_forward(const ct_conv_desc* d, void* stream) {
+  CT_REQUIRE(d && d->x && d->w && d->out, "null pointer");
+  CT_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->C_in > 0 && d->C_out > 0, "bad shape");
+  CT_REQUIRE(d->OH == (d->H + 2 * d->pad - d->KH) / d->stride + 1, "OH inconsistent");
+  CT_REQUIRE(d->OW == (d->W + 2 * d->pad - d->KW) / d->stride + 1, "OW inconsistent");
+  CT_REQUIRE(d->ld_in >= d->C_in, "ld_in < C_in");
+  CT_REQUIRE(d->out_mode == CT_OUT_NCHW_F32 || d->ld_out >= d->C_out, "ld_out < C_out");
+  if (d->a_mode == CT_A_DCN) {
+    CT_REQUIRE(d->om != nullptr && d->ld_om >= 27, "DCN needs om with ld_om >= 27");
+    CT_REQUIRE(d->KH == 3 && d->KW == 3 && d->stride == 1 && d->pad == 1, "DCN is 3x3 s1 p1");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->engine == CT_ENGINE_SIMT) return conv_forward_simt(d, st);
+  if (d->engine == CT_ENGINE_TCGEN05) {
+    CT_REQUIRE(d->dtype == CT_BF16, "tcgen05 engine needs bf16 activations");
+    return conv_forward_tc(d, st);
+  }
+  return fail(CT_ERR_INVALID, "unknown engine%s %ld", "", (long)d->engine);
+}

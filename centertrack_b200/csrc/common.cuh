@@ -1,0 +1,64 @@
+// Shared helpers for libctb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/ctb200.h"
+
+namespace ctb {
+
+extern thread_local char g_err[512];
+extern thread_local int64_t g_launches;
+
+inline int fail(int code, const char* fmt, const char* a = "", long b = 0, long c = 0) {
+  snprintf(g_err, sizeof(g_err), fmt, a, b, c);
+  return code;
+}
+
+#define CT_REQUIRE(cond, msg)                                                      \
+  do {                                                                             \
+    if (!(cond)) return ctb::fail(CT_ERR_INVALID, "%s: requirement failed: " msg " (%ld,%ld)", \
+                                  __func__, 0, 0);                                 \
+  } while (0)
+
+#define CT_CUDA_OK(expr)                                                            \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess)                                                         \
+      return ctb::fail(CT_ERR_CUDA, "%s: CUDA error %ld at line %ld", cudaGetErrorString(_e), \
+                       (long)_e, (long)__LINE__);                                  \
+  } while (0)
+
+inline int after_launch() {
+  ++g_launches;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(CT_ERR_CUDA, "kernel launch failed: %s (%ld)", cudaGetErrorString(e), (long)e);
+  }
+  return CT_OK;
+}
+
+// ---- element type helpers -----------------------------------------------------------
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+  static __device__ __forceinline__ float ld(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+};
+template <> struct Elem<__nv_bfloat16> {
+  static __device__ __forceinline__ float ld(const __nv_bfloat16* p) {
+    return __bfloat162float(*p);
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) {
+    *p = __float2bfloat16_rn(v);
+  }
+};
+
+__device__ __forceinline__ float sigmoidf_ref(float x) {
+  // same formula as ATen's CPU/CUDA sigmoid: 1 / (1 + exp(-x)), fp32, IEEE division
+  return 1.0f / (1.0f + expf(-x));
+}
+
+}  // namespace ctb

@@ -1,0 +1,436 @@
+// tcgen05 implicit-GEMM convolution / DCNv2 for sm_100a (bf16 operands, fp32 accumulate in TMEM).
+//
+//   D[128 pixels x n_tile channels] (TMEM)  +=  A[128 x 64] (smem, gathered)  x  B[n_tile x 64]^T (smem)
+//
+// * No im2row buffer in HBM: producer warps gather each 64-wide K slice (tap-major, k = tap*C_in + c)
+//   of the A operand straight into the 128B-swizzled K-major shared-memory layout the UMMA smem
+//   descriptor expects.  For CT_A_DCN the gather is the DCNv2 bilinear sample x mask (the reference's
+//   `columns` tensor never exists).
+// * Weights are pre-packed on the host as ready-made swizzled tile images, so one TMA bulk copy
+//   (cp.async.bulk, mbarrier complete_tx) per K slice brings the B tile.
+// * One elected thread issues tcgen05.mma (M=128, N=n_tile, K=16) x4 per slice; tcgen05.commit
+//   releases the smem stage back to the producers and finally signals the epilogue.
+// * Epilogue: tcgen05.ld (32 lanes x 16 columns per warp), + folded-BN shift, + residual, ReLU,
+//   then bf16 NHWC / fp32 NHWC (DCN offsets, sigmoid on the mask channels) / fp32 NCHW (heads,
+//   sigmoid / depth transform) stores.
+//
+// CTA = 160 threads: warps 0-3 producers then epilogue (warp w owns TMEM lanes 32w..32w+31),
+// warp 4 = TMEM allocator + MMA issuer.  Several CTAs are co-resident per SM (<= 512 TMEM columns)
+// so one CTA's epilogue overlaps another's main loop.
+#include "conv_common.cuh"
+
+namespace ctb {
+
+constexpr int TC_BM = 128;           // output pixels per CTA (UMMA M)
+constexpr int TC_BK = 64;            // K elements per pipeline stage (one 128B swizzle atom of bf16)
+constexpr int TC_THREADS = 160;
+constexpr int TC_PRODUCERS = 128;
+constexpr int A_STAGE_BYTES = TC_BM * 128;
+
+struct TcArgs {
+  ConvGeom g;
+  const __nv_bfloat16* x;
+  const __nv_bfloat16* w;       // packed tiles
+  const float* shift;
+  const __nv_bfloat16* residual;
+  const float* om;
+  void* out;
+  int n_tile, k_slices, stages, tmem_cols, a_mode;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > 20000000u) __trap();   // watchdog: a protocol bug must not hang the GPU
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint4 ldg_nc16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void sts16(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// K-major, 128B-swizzled smem operand descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (=64: 8 rows x 128B)
+//   [46,48) version=1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, K-major both.
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+struct __align__(16) DcnEntry { short y0, x0; float ly, lx, m; };   // 16 bytes
+
+__device__ __forceinline__ void blend8(float (&acc)[8], uint4 v, float w) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float2 f = __bfloat1622float2(h[q]);
+    acc[2 * q] = fmaf(w, f.x, acc[2 * q]);
+    acc[2 * q + 1] = fmaf(w, f.y, acc[2 * q + 1]);
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS)
+conv_tc_kernel(const TcArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  // SWIZZLE_128B operands need 1024B-aligned stage bases: align by hand (launch adds 1 KB of slack)
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const ConvGeom& g = a.g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = a.stages;
+  const uint32_t b_stage_bytes = (uint32_t)a.n_tile * 128u;
+
+  // carve shared memory
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t sA = smem_base;
+  const uint32_t sB = sA + S * A_STAGE_BYTES;
+  const uint32_t off_bar = S * A_STAGE_BYTES + S * b_stage_bytes;
+  const uint32_t bars = smem_base + off_bar;           // full[S], empty[S], tmem_full
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + off_bar + (2 * S + 1) * 8);
+  DcnEntry* dcn_tab = reinterpret_cast<DcnEntry*>(smem + off_bar + (2 * S + 1) * 8 + 8);  // 16B aligned
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (2 * S);
+
+  const int m0 = blockIdx.x * TC_BM;
+  const int nt = blockIdx.y;
+  const int n0 = nt * a.n_tile;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), TC_PRODUCERS); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32((const void*)tmem_slot)),
+                 "r"((uint32_t)a.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // =========================== A producers ===========================
+    const int q = tid & 7;                 // 16-byte chunk (8 channels) inside the 64-wide K slice
+    const int r0 = tid >> 3;               // rows r0 + 16*i
+    const uint32_t swz = (uint32_t)((q ^ (r0 & 7)) << 4);
+    const int HWo = g.OH * g.OW;
+    int row_img[8], row_iy[8], row_ix[8];   // image base pixel, top-left input coords of the window
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int p = m0 + r0 + 16 * i;
+      if (p < g.P_out) {
+        const int b = p / HWo, r = p - b * HWo;
+        const int oy = r / g.OW, ox = r - oy * g.OW;
+        row_img[i] = b * g.H * g.W;
+        row_iy[i] = oy * g.stride - g.pad;
+        row_ix[i] = ox * g.stride - g.pad;
+      } else {
+        row_img[i] = 0; row_iy[i] = -100000; row_ix[i] = -100000;
+      }
+    }
+    if (a.a_mode == CT_A_DCN) {
+      // per (tap,row) sampling parameters, computed once per CTA (row = tid)
+      const int p = m0 + tid;
+      const bool ok = p < g.P_out;
+      int oy = 0, ox = 0;
+      if (ok) { const int r = p % HWo; oy = r / g.OW; ox = r - oy * g.OW; }
+      const float* omp = a.om + (size_t)(ok ? p : 0) * g.ld_om;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        DcnEntry e; e.y0 = 0; e.x0 = 0; e.ly = 0.f; e.lx = 0.f; e.m = 0.f;
+        if (ok) {
+          const float py = (float)(oy - 1 + tap / 3) + __ldg(omp + 2 * tap);
+          const float px = (float)(ox - 1 + tap % 3) + __ldg(omp + 2 * tap + 1);
+          if (py > -1.f && py < (float)g.H && px > -1.f && px < (float)g.W) {
+            const float y0f = floorf(py), x0f = floorf(px);
+            e.y0 = (short)(int)y0f; e.x0 = (short)(int)x0f;
+            e.ly = py - y0f; e.lx = px - x0f; e.m = __ldg(omp + 18 + tap);
+          }
+        }
+        dcn_tab[tap * TC_BM + tid] = e;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    const int cin8 = g.C_in >> 3;
+    const int ntaps = g.KH * g.KW;
+    const __nv_bfloat16* wt = a.w + (size_t)nt * a.k_slices * a.n_tile * TC_BK;
+
+    for (int s = 0; s < a.k_slices; ++s) {
+      const int stage = s % S;
+      const uint32_t ph = (uint32_t)(s / S) & 1u;
+      mbar_wait(empty_bar(stage), ph ^ 1u);
+      if (tid == 0) {
+        mbar_expect_tx(full_bar(stage), b_stage_bytes);
+        bulk_g2s(sB + stage * b_stage_bytes, wt + (size_t)s * a.n_tile * TC_BK, b_stage_bytes, full_bar(stage));
+      }
+      const int kc = s * 8 + q;
+      const int tap = kc / cin8;
+      const int c = (kc - tap * cin8) << 3;
+      const uint32_t dst = sA + stage * A_STAGE_BYTES + (uint32_t)r0 * 128u + swz;
+      if (tap >= ntaps) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sts16(dst + i * 2048u, make_uint4(0, 0, 0, 0));
+      } else if (a.a_mode == CT_A_CONV) {
+        const int ky = tap / g.KW, kx = tap - ky * g.KW;
+        uint4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int iy = row_iy[i] + ky, ix = row_ix[i] + kx;
+          v[i] = make_uint4(0, 0, 0, 0);
+          if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
+            v[i] = ldg_nc16(a.x + ((size_t)(row_img[i] + iy * g.W + ix)) * g.ld_in + c);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sts16(dst + i * 2048u, v[i]);
+      } else {
+        const DcnEntry* tab = dcn_tab + tap * TC_BM + r0;
+#pragma unroll 2
+        for (int i = 0; i < 8; ++i) {
+          const DcnEntry e = tab[16 * i];
+          float acc[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+          if (e.m != 0.f) {
+            const int y0 = e.y0, x0 = e.x0;
+            const float hy = 1.f - e.ly, hx = 1.f - e.lx;
+            const bool y0ok = y0 >= 0, y1ok = y0 + 1 <= g.H - 1;
+            const bool x0ok = x0 >= 0, x1ok = x0 + 1 <= g.W - 1;
+            const __nv_bfloat16* base = a.x + ((size_t)(row_img[i] + y0 * g.W + x0)) * g.ld_in + c;
+            uint4 v00 = make_uint4(0, 0, 0, 0), v01 = v00, v10 = v00, v11 = v00;
+            if (y0ok && x0ok) v00 = ldg_nc16(base);
+            if (y0ok && x1ok) v01 = ldg_nc16(base + g.ld_in);
+            if (y1ok && x0ok) v10 = ldg_nc16(base + (size_t)g.W * g.ld_in);
+            if (y1ok && x1ok) v11 = ldg_nc16(base + (size_t)(g.W + 1) * g.ld_in);
+            blend8(acc, v00, hy * hx * e.m);
+            blend8(acc, v01, hy * e.lx * e.m);
+            blend8(acc, v10, e.ly * hx * e.m);
+            blend8(acc, v11, e.ly * e.lx * e.m);
+          }
+          uint4 o;
+          __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+          sts16(dst + i * 2048u, o);
+        }
+      }
+      fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+      mbar_arrive(full_bar(stage));
+    }
+
+    // =========================== epilogue ===========================
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+    const int p = m0 + row;
+    const bool p_ok = p < g.P_out;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int col = 0; col < a.n_tile; col += 16) {
+      uint32_t r[16];
+      tc_ld16(t_lane + (uint32_t)col, r);
+      const int o0 = n0 + col;
+      if (!p_ok || o0 >= g.C_out) continue;
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+      if (a.shift) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) if (o0 + j < g.C_out) v[j] += __ldg(a.shift + o0 + j);
+      }
+      if (g.out_mode == CT_OUT_NHWC) {
+        if (a.residual) {
+          const uint4* rp = reinterpret_cast<const uint4*>(a.residual + (size_t)p * g.ld_res + o0);
+          const uint4 ra = ldg_nc16(rp), rb = ldg_nc16(rp + 1);
+          const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&ra);
+          const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&rb);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 fa = __bfloat1622float2(ha[j]), fb = __bfloat1622float2(hb[j]);
+            v[2 * j] += fa.x; v[2 * j + 1] += fa.y; v[8 + 2 * j] += fb.x; v[8 + 2 * j + 1] += fb.y;
+          }
+        }
+        if (g.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        uint4 oa, ob;
+        __nv_bfloat162* pa = reinterpret_cast<__nv_bfloat162*>(&oa);
+        __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&ob);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          pa[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+          pb[j] = __floats2bfloat162_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
+        }
+        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + (size_t)p * g.ld_out + o0);
+        op[0] = oa; op[1] = ob;
+      } else if (g.out_mode == CT_OUT_NHWC_F32) {
+        float* op = reinterpret_cast<float*>(a.out) + (size_t)p * g.ld_out + o0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (o0 + j < g.C_out) {
+            float t = v[j];
+            if (g.relu) t = fmaxf(t, 0.f);
+            if (o0 + j >= g.sig_from) t = sigmoidf_ref(t);
+            op[j] = t;
+          }
+        }
+      } else {
+        const int b = p / HWo, rr = p - b * HWo;
+        float* op = reinterpret_cast<float*>(a.out) + ((size_t)b * g.C_out + o0) * HWo + rr;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (o0 + j < g.C_out) {
+            float t = v[j];
+            if (g.relu) t = fmaxf(t, 0.f);
+            op[(size_t)j * HWo] = head_transform(t, g.head_act, g.depth_scale);
+          }
+        }
+      }
+    }
+  } else if (lane == 0) {
+    // =========================== MMA issuer (one thread) ===========================
+    const uint32_t idesc = make_idesc(a.n_tile);
+    for (int s = 0; s < a.k_slices; ++s) {
+      const int stage = s % S;
+      const uint32_t ph = (uint32_t)(s / S) & 1u;
+      mbar_wait(full_bar(stage), ph);
+      tc_fence_after();
+      const uint64_t ad = make_sdesc(sA + stage * A_STAGE_BYTES);
+      const uint64_t bd = make_sdesc(sB + stage * b_stage_bytes);
+#pragma unroll
+      for (int k = 0; k < TC_BK / 16; ++k)
+        tc_mma(tmem_base, ad + 2ull * k, bd + 2ull * k, idesc, (s > 0 || k > 0) ? 1u : 0u);
+      tc_commit(empty_bar(stage));     // frees this smem stage when the MMAs above have read it
+    }
+    tc_commit(tmem_full_bar);           // accumulator complete -> epilogue
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols)
+                 : "memory");
+  }
+}
+
+int conv_forward_tc(const ct_conv_desc* d, cudaStream_t st) {
+  TcArgs a;
+  a.g = make_geom(d);
+  const ConvGeom& g = a.g;
+  if (g.C_in % 8 != 0 || g.ld_in % 8 != 0)
+    return fail(CT_ERR_INVALID, "conv_tc: C_in and ld_in must be multiples of 8%s (%ld,%ld)", "", g.C_in, g.ld_in);
+  if (((uintptr_t)d->x & 15) || ((uintptr_t)d->w & 15) || ((uintptr_t)d->out & 15))
+    return fail(CT_ERR_INVALID, "conv_tc: x/w/out must be 16-byte aligned%s", "");
+  int n_tile = d->n_tile;
+  if (n_tile <= 0 || n_tile % 16 != 0 || n_tile > 256)
+    return fail(CT_ERR_INVALID, "conv_tc: n_tile must be a multiple of 16 in [16,256]%s (%ld)", "", n_tile);
+  if (g.out_mode == CT_OUT_NHWC) {
+    if (g.C_out % 16 != 0 || g.ld_out % 8 != 0)
+      return fail(CT_ERR_INVALID, "conv_tc: NHWC bf16 output needs C_out %% 16 == 0 and ld_out %% 8 == 0%s", "");
+    if (d->residual && (g.ld_res % 8 != 0 || ((uintptr_t)d->residual & 15)))
+      return fail(CT_ERR_INVALID, "conv_tc: residual must be 16B aligned with ld_res %% 8 == 0%s", "");
+  } else if (g.out_mode == CT_OUT_NHWC_F32) {
+    if (d->residual) return fail(CT_ERR_INVALID, "conv_tc: residual unsupported for fp32 outputs%s", "");
+  } else if (d->residual) {
+    return fail(CT_ERR_INVALID, "conv_tc: residual unsupported for fp32 outputs%s", "");
+  }
+  if (g.H > 32767 || g.W > 32767) return fail(CT_ERR_INVALID, "conv_tc: image too large%s", "");
+  a.x = (const __nv_bfloat16*)d->x;
+  a.w = (const __nv_bfloat16*)d->w;
+  a.shift = d->shift;
+  a.residual = (const __nv_bfloat16*)d->residual;
+  a.om = d->om;
+  a.out = d->out;
+  a.n_tile = n_tile;
+  a.k_slices = (g.K_total + TC_BK - 1) / TC_BK;
+  a.a_mode = d->a_mode;
+  int cols = 32;
+  while (cols < n_tile) cols <<= 1;
+  a.tmem_cols = cols;
+  auto smem_for = [&](int stg) {
+    return (size_t)stg * (A_STAGE_BYTES + n_tile * 128) + (2 * stg + 1) * 8 + 16 +
+           (d->a_mode == CT_A_DCN ? 9 * TC_BM * sizeof(DcnEntry) : 0) + 1024;
+  };
+  int stages = 4;                                   // keep >= 2 CTAs per SM when the tile allows it
+  if (smem_for(stages) > 112 * 1024) stages = 3;
+  if (stages > a.k_slices) stages = a.k_slices;
+  a.stages = stages;
+  const size_t smem = smem_for(stages);
+  static thread_local size_t smem_set = 0;
+  if (smem > smem_set) {
+    CT_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    smem_set = 200 * 1024;
+  }
+  const int n_tiles = (g.C_out + n_tile - 1) / n_tile;
+  dim3 grid((g.P_out + TC_BM - 1) / TC_BM, n_tiles);
+  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(a);
+  return after_launch();
+}
+
+}  // namespace ctb

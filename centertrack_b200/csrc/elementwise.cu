@@ -1,0 +1,219 @@
+// Bandwidth-bound pieces of the DLA-34 path: the three 7x7 stems (reference NCHW fp32 inputs in,
+// NHWC activations out), Tree.downsample (2x2 max-pool), IDAUp's depthwise transposed-conv
+// upsample fused with the skip add, and the pre_hm gaussian splat.
+#include "common.cuh"
+
+namespace ctb {
+
+// ------------------------------------------------------------------------------------------
+// stem: out = relu(bn(conv7(img))) + relu(bn(conv7(pre_img))) + relu(bn(conv7(pre_hm)))
+// (dla.py:238-242,256-267,305-311 -- note ReLU is applied per stem BEFORE the sum)
+// ------------------------------------------------------------------------------------------
+constexpr int ST = 16;            // 16x16 output pixels per CTA
+constexpr int SH = ST + 6;        // halo side
+
+template <typename T>
+__global__ void __launch_bounds__(ST * ST)
+stem_kernel(const float* __restrict__ img, const float* __restrict__ pre, const float* __restrict__ hm,
+            const float* __restrict__ w, const float* __restrict__ shift, T* __restrict__ out,
+            int B, int H, int W, int ld_out) {
+  __shared__ float halo[7][SH][SH + 1];
+  __shared__ __align__(16) float ws[49 * 7 * 16];
+  const int tx = threadIdx.x % ST, ty = threadIdx.x / ST;
+  const int x0 = blockIdx.x * ST, y0 = blockIdx.y * ST, b = blockIdx.z;
+  const size_t plane = (size_t)H * W;
+  for (int i = threadIdx.x; i < 49 * 7 * 16; i += ST * ST) ws[i] = w[i];
+  for (int i = threadIdx.x; i < 7 * SH * SH; i += ST * ST) {
+    const int ch = i / (SH * SH), r = i % (SH * SH), hy = r / SH, hx = r % SH;
+    const int gy = y0 + hy - 3, gx = x0 + hx - 3;
+    float v = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      if (ch < 3) v = __ldg(img + ((size_t)b * 3 + ch) * plane + (size_t)gy * W + gx);
+      else if (ch < 6) { if (pre) v = __ldg(pre + ((size_t)b * 3 + ch - 3) * plane + (size_t)gy * W + gx); }
+      else { if (hm) v = __ldg(hm + (size_t)b * plane + (size_t)gy * W + gx); }
+    }
+    halo[ch][hy][hx] = v;
+  }
+  __syncthreads();
+  float a0[16], a1[16], a2[16];
+#pragma unroll
+  for (int o = 0; o < 16; ++o) { a0[o] = 0.f; a1[o] = 0.f; a2[o] = 0.f; }
+  for (int ky = 0; ky < 7; ++ky) {
+#pragma unroll
+    for (int kx = 0; kx < 7; ++kx) {
+      const float* wt = ws + (ky * 7 + kx) * 7 * 16;
+#pragma unroll
+      for (int ch = 0; ch < 7; ++ch) {
+        const float v = halo[ch][ty + ky][tx + kx];
+        const float4* w4 = reinterpret_cast<const float4*>(wt + ch * 16);
+        float* acc = ch < 3 ? a0 : (ch < 6 ? a1 : a2);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 ww = w4[q];
+          acc[q * 4 + 0] = fmaf(v, ww.x, acc[q * 4 + 0]);
+          acc[q * 4 + 1] = fmaf(v, ww.y, acc[q * 4 + 1]);
+          acc[q * 4 + 2] = fmaf(v, ww.z, acc[q * 4 + 2]);
+          acc[q * 4 + 3] = fmaf(v, ww.w, acc[q * 4 + 3]);
+        }
+      }
+    }
+  }
+  const int gy = y0 + ty, gx = x0 + tx;
+  if (gy < H && gx < W) {
+    T* o = out + ((size_t)b * plane + (size_t)gy * W + gx) * ld_out;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      float v = fmaxf(a0[c] + shift[c], 0.f);
+      if (pre) v += fmaxf(a1[c] + shift[16 + c], 0.f);
+      if (hm) v += fmaxf(a2[c] + shift[32 + c], 0.f);
+      Elem<T>::st(o + c, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void maxpool2_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, int W, int C,
+                                int ld_in, int ld_out) {
+  const int OH = H / 2, OW = W / 2;
+  const size_t total = (size_t)B * OH * OW * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int c = i % C;
+    size_t p = i / C;
+    const int ox = p % OW; p /= OW;
+    const int oy = p % OH;
+    const int b = p / OH;
+    const T* s = x + (((size_t)b * H + 2 * oy) * W + 2 * ox) * ld_in + c;
+    const float v = fmaxf(fmaxf(Elem<T>::ld(s), Elem<T>::ld(s + ld_in)),
+                          fmaxf(Elem<T>::ld(s + (size_t)W * ld_in), Elem<T>::ld(s + (size_t)(W + 1) * ld_in)));
+    Elem<T>::st(out + (((size_t)b * OH + oy) * OW + ox) * ld_out + c, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// depthwise ConvTranspose2d(k=2f, stride f, pad f/2, no bias) + skip  (dla.py:529-531,543-545)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void upsample_add_kernel(const T* __restrict__ x, const T* __restrict__ skip,
+                                    const float* __restrict__ w, T* __restrict__ out, int B, int H, int W,
+                                    int C, int f, int ld_in, int ld_skip, int ld_out) {
+  const int OH = H * f, OW = W * f, pad = f / 2, k = 2 * f;
+  const size_t total = (size_t)B * OH * OW * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int c = i % C;
+    size_t p = i / C;
+    const int ox = p % OW; p /= OW;
+    const int oy = p % OH;
+    const int b = p / OH;
+    float acc = 0.f;
+    const int iy_hi = (oy + pad) / f, ix_hi = (ox + pad) / f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const int iy = iy_hi - dy;
+      const int ky = oy + pad - iy * f;
+      if (iy < 0 || iy >= H || ky >= k) continue;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int ix = ix_hi - dx;
+        const int kx = ox + pad - ix * f;
+        if (ix < 0 || ix >= W || kx >= k) continue;
+        acc = fmaf(Elem<T>::ld(x + (((size_t)b * H + iy) * W + ix) * ld_in + c),
+                   __ldg(w + ((size_t)c * k + ky) * k + kx), acc);
+      }
+    }
+    const size_t op = ((size_t)b * OH + oy) * OW + ox;
+    if (skip) acc += Elem<T>::ld(skip + op * ld_skip + c);
+    Elem<T>::st(out + op * ld_out + c, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// pre_hm splat: draw_umich_gaussian image.py:128-154 (gaussian2D in float64, np.maximum)
+// ------------------------------------------------------------------------------------------
+__global__ void render_pre_hm_kernel(const float* __restrict__ boxes, int n, float* __restrict__ hm,
+                                     int B, int H, int W) {
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  const int b = (int)boxes[i * 5 + 0], cx = (int)boxes[i * 5 + 1], cy = (int)boxes[i * 5 + 2];
+  const int r = (int)boxes[i * 5 + 3];
+  if (b < 0 || b >= B) return;
+  const double sigma = (double)(2 * r + 1) / 6.0;
+  const int left = min(cx, r), right = min(W - cx, r + 1), top = min(cy, r), bottom = min(H - cy, r + 1);
+  const int w = left + right, h = top + bottom;
+  if (w <= 0 || h <= 0) return;
+  for (int j = threadIdx.x; j < w * h; j += blockDim.x) {
+    const int yy = j / w - top, xx = j % w - left;
+    double v = exp(-(double)(xx * xx + yy * yy) / (2.0 * sigma * sigma));
+    if (v < 2.220446049250313e-16) v = 0.0;
+    const float fv = (float)v;
+    atomicMax(reinterpret_cast<int*>(hm + ((size_t)b * H + cy + yy) * W + cx + xx), __float_as_int(fv));
+  }
+}
+
+}  // namespace ctb
+
+using namespace ctb;
+
+extern "C" int ct_stem_forward(const float* img, const float* pre_img, const float* pre_hm, const float* w,
+                               const float* shift, void* out, int32_t dtype, int32_t B, int32_t H,
+                               int32_t W, int32_t ld_out, void* stream) {
+  CT_REQUIRE(img && w && shift && out, "null pointer");
+  CT_REQUIRE(B > 0 && H > 0 && W > 0 && ld_out >= 16, "bad shape");
+  dim3 grid((W + ST - 1) / ST, (H + ST - 1) / ST, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == CT_F32)
+    stem_kernel<float><<<grid, ST * ST, 0, st>>>(img, pre_img, pre_hm, w, shift, (float*)out, B, H, W, ld_out);
+  else
+    stem_kernel<__nv_bfloat16><<<grid, ST * ST, 0, st>>>(img, pre_img, pre_hm, w, shift,
+                                                         (__nv_bfloat16*)out, B, H, W, ld_out);
+  return after_launch();
+}
+
+static inline int ew_blocks(size_t total) {
+  size_t b = (total + 255) / 256;
+  return (int)(b < 148 * 16 ? (b ? b : 1) : 148 * 16);
+}
+
+extern "C" int ct_maxpool2(const void* x, void* out, int32_t dtype, int32_t B, int32_t H, int32_t W,
+                           int32_t C, int32_t ld_in, int32_t ld_out, void* stream) {
+  CT_REQUIRE(x && out, "null pointer");
+  CT_REQUIRE(H % 2 == 0 && W % 2 == 0, "odd spatial size");
+  const size_t total = (size_t)B * (H / 2) * (W / 2) * C;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == CT_F32)
+    maxpool2_kernel<float><<<ew_blocks(total), 256, 0, st>>>((const float*)x, (float*)out, B, H, W, C, ld_in, ld_out);
+  else
+    maxpool2_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, st>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)out, B, H, W, C, ld_in, ld_out);
+  return after_launch();
+}
+
+extern "C" int ct_upsample_add(const void* x, const void* skip, const float* w, void* out, int32_t dtype,
+                               int32_t B, int32_t H, int32_t W, int32_t C, int32_t f, int32_t ld_in,
+                               int32_t ld_skip, int32_t ld_out, void* stream) {
+  CT_REQUIRE(x && w && out, "null pointer");
+  CT_REQUIRE(f == 2 || f == 4 || f == 8, "unsupported upsample factor");
+  const size_t total = (size_t)B * H * f * W * f * C;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == CT_F32)
+    upsample_add_kernel<float><<<ew_blocks(total), 256, 0, st>>>(
+        (const float*)x, (const float*)skip, w, (float*)out, B, H, W, C, f, ld_in, ld_skip, ld_out);
+  else
+    upsample_add_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, st>>>(
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)skip, w, (__nv_bfloat16*)out, B, H, W, C, f,
+        ld_in, ld_skip, ld_out);
+  return after_launch();
+}
+
+extern "C" int ct_render_pre_hm(const float* boxes, int32_t n, float* pre_hm, int32_t B, int32_t H,
+                                int32_t W, void* stream) {
+  CT_REQUIRE(pre_hm, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  CT_CUDA_OK(cudaMemsetAsync(pre_hm, 0, (size_t)B * H * W * sizeof(float), st));
+  if (n <= 0) return CT_OK;
+  CT_REQUIRE(boxes, "null boxes");
+  render_pre_hm_kernel<<<n, 256, 0, st>>>(boxes, n, pre_hm, B, H, W);
+  return after_launch();
+}

@@ -1,0 +1,188 @@
+/* ctb200.h -- C ABI of libctb200.so: the B200 (sm_100a) implementation of CenterTrack's
+ * per-frame inference hot path.  Plain C: raw device pointers, sizes, a cudaStream_t passed
+ * as void*; every entry point returns 0 on success or a negative ct_status and never throws.
+ * No ownership transfer: the caller (the Python shims in centertrack_b200/, which allocate
+ * through torch) owns every buffer.  Thread-compatible: no global mutable state other than
+ * the per-thread last-error string.
+ *
+ * Reference interfaces each entry point replaces (paths relative to the reference's src/lib):
+ *   ct_conv_forward   nn.Conv2d+BatchNorm2d(+residual)+ReLU chains of DLA-34: dla.py:38-66
+ *                     (BasicBlock), 154-172 (Root), 293-303 (_make_conv_level), 212-218
+ *                     (Tree.project); head convs base_model.py:27-38; and, with
+ *                     mode=CT_A_DCN, the absent DCNv2 extension's DCN.forward that
+ *                     dla.py:513,516 calls (modulated deformable conv v2, 3x3/s1/p1/dg1).
+ *   ct_stem_forward   DLA.forward's three 7x7 stems, dla.py:238-242,256-267,305-311.
+ *   ct_maxpool2       nn.MaxPool2d(2,2) = Tree.downsample, dla.py:207.
+ *   ct_upsample_add   IDAUp's depthwise ConvTranspose2d + skip add, dla.py:529-531,543-545.
+ *   ct_decode         Detector.process's decode half: _nms + _topk + _tranpose_and_gather_feat
+ *                     + generic_decode, utils.py:16-26,52-87 and decode.py:83-182
+ *                     (+ _update_kps_with_hm decode.py:11-81 for the pose heads).
+ *   ct_render_pre_hm  Detector._get_additional_inputs's gaussian splat, detector.py:254-290.
+ */
+#ifndef CTB200_H_
+#define CTB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTB200_ABI_VERSION 1
+
+typedef enum {
+  CT_OK = 0,
+  CT_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+  CT_ERR_CUDA = -2,        /* a CUDA runtime call failed (see ct_last_error) */
+  CT_ERR_UNSUPPORTED = -3  /* valid request this build cannot serve */
+} ct_status;
+
+typedef enum { CT_F32 = 0, CT_BF16 = 1 } ct_dtype;
+
+/* How the A operand (rows = output pixels, K = taps x C_in) of the implicit GEMM is formed. */
+typedef enum {
+  CT_A_CONV = 0,  /* plain KxK window, stride/pad */
+  CT_A_DCN = 1    /* 3x3 s1 p1 modulated-deformable bilinear sampling driven by `om` */
+} ct_a_mode;
+
+/* Epilogue / output format. */
+typedef enum {
+  CT_OUT_NHWC = 0,       /* out[p*ld_out + o], activation dtype */
+  CT_OUT_NHWC_F32 = 1,   /* fp32 NHWC (DCN offset/mask map; sigmoid on channels >= sig_from) */
+  CT_OUT_NCHW_F32 = 2    /* fp32 [B,C_out,H,W] planes (head outputs, reference layout) */
+} ct_out_mode;
+
+typedef enum {           /* per-launch transform applied to the fp32 NCHW head outputs */
+  CT_HEAD_NONE = 0,
+  CT_HEAD_SIGMOID = 1,   /* hm, hm_hp: detector.py:301-304 */
+  CT_HEAD_DEPTH = 2      /* dep = 1/(sigmoid(x)+1e-6)-1, times depth_scale: detector.py:305-307 */
+} ct_head_act;
+
+typedef enum { CT_ENGINE_SIMT = 0, CT_ENGINE_TCGEN05 = 1 } ct_engine;
+
+/* One convolution-like layer.  Activations are NHWC with an explicit pixel stride (ld, in
+ * elements) so that a producer can write straight into a channel slice of a concat buffer
+ * (DLA Root nodes, dla.py:167) and a consumer can read a slice back. */
+typedef struct {
+  int32_t engine;        /* ct_engine */
+  int32_t dtype;         /* ct_dtype of activations in/out (CT_ENGINE_TCGEN05 requires CT_BF16) */
+  int32_t a_mode;        /* ct_a_mode */
+  int32_t B, H, W;       /* input batch / spatial size */
+  int32_t C_in, ld_in;   /* input channels used, input pixel stride */
+  int32_t C_out;         /* real output channels */
+  int32_t KH, KW, stride, pad;
+  int32_t OH, OW;        /* output spatial size */
+  int32_t ld_out;        /* output pixel stride (CT_OUT_NHWC*) */
+  int32_t out_mode;      /* ct_out_mode */
+  int32_t relu;          /* 1: ReLU after shift (+residual) */
+  int32_t ld_res;        /* residual pixel stride (residual may be NULL) */
+  int32_t head_act;      /* ct_head_act (CT_OUT_NCHW_F32 only) */
+  int32_t sig_from;      /* CT_OUT_NHWC_F32: sigmoid applied to channels >= sig_from (DCN mask) */
+  float   depth_scale;
+  int32_t ld_om;         /* CT_A_DCN: pixel stride of `om` (fp32 NHWC, >= 27) */
+  int32_t n_tile;        /* tcgen05: output-channel tile (multiple of 16, <= 256); 0 = auto */
+  const void* x;         /* input activations */
+  const void* w;         /* packed weights: see ct_pack_weights */
+  const float* shift;    /* [C_out] folded BN shift / conv bias (may be NULL) */
+  const void* residual;  /* [P_out, ld_res] same dtype as activations, or NULL */
+  const float* om;       /* CT_A_DCN: offsets (ch 0..17, 2k=dy 2k+1=dx) + sigmoid'd mask (18..26) */
+  void* out;
+} ct_conv_desc;
+
+/* Size in bytes of the packed weight blob ct_pack_weights produces for this engine/shape. */
+int64_t ct_packed_weight_bytes(int32_t engine, int32_t C_out, int32_t C_in, int32_t KH, int32_t KW,
+                               int32_t n_tile);
+/* Host-side packing.  w_oihw: fp32 [C_out, C_in, KH, KW] (already BN-scale-folded).
+ * SIMT engine : fp32 [KH*KW*C_in (k = tap*C_in + c)][C_out_pad16].
+ * tcgen05     : bf16 tiles [n_tiles][k_slices][n_tile rows x 64 k] in the 128B-swizzled
+ *               shared-memory image the MMA descriptor expects (one bulk copy per tile). */
+int ct_pack_weights(int32_t engine, const float* w_oihw, int32_t C_out, int32_t C_in, int32_t KH,
+                    int32_t KW, int32_t n_tile, void* dst);
+
+int ct_conv_forward(const ct_conv_desc* d, void* stream);
+
+/* Three 7x7 stems on reference-layout inputs (fp32 NCHW):
+ *   out = relu(bn(conv7(img))) + relu(bn(conv7(pre_img))) + relu(bn(conv7(pre_hm)))
+ * w: fp32 [49 taps][7 in-ch (img0..2, pre0..2, hm)][16] BN-scale-folded; shift: [3][16].
+ * pre_img / pre_hm may be NULL (dla.py:308-311).  out: NHWC [B,H,W,16] of `dtype`. */
+int ct_stem_forward(const float* img, const float* pre_img, const float* pre_hm, const float* w,
+                    const float* shift, void* out, int32_t dtype, int32_t B, int32_t H, int32_t W,
+                    int32_t ld_out, void* stream);
+
+int ct_maxpool2(const void* x, void* out, int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t C,
+                int32_t ld_in, int32_t ld_out, void* stream);
+
+/* out[b,oy,ox,c] = skip[...] + sum_{ky,kx} x[b,(oy+pad-ky)/f,(ox+pad-kx)/f,c] * w[c,ky,kx]
+ * (depthwise ConvTranspose2d, kernel 2f, stride f, pad f/2; w fp32 [C][2f][2f]). */
+int ct_upsample_add(const void* x, const void* skip, const float* w, void* out, int32_t dtype,
+                    int32_t B, int32_t H, int32_t W, int32_t C, int32_t f, int32_t ld_in,
+                    int32_t ld_skip, int32_t ld_out, void* stream);
+
+/* ---- decode ------------------------------------------------------------------------- */
+#define CT_DECODE_MAX_HEADS 12
+typedef enum {          /* role of a gathered regression map in generic_decode */
+  CT_ROLE_RAW = 0,      /* copied as-is (tracking, dep, rot, dim, amodel_offset, ...) */
+  CT_ROLE_REG = 1,      /* center offset: xs = xs0 + reg_x (decode.py:103-108) */
+  CT_ROLE_WH = 2,       /* clamped >= 0, makes bboxes (decode.py:113-129) */
+  CT_ROLE_LTRB = 3,     /* bboxes = ct0 + ltrb (decode.py:132-139) */
+  CT_ROLE_LTRB_AMODAL = 4, /* bboxes_amodal, overrides bboxes (decode.py:150-159) */
+  CT_ROLE_HPS = 5       /* keypoint offsets: += xs0/ys0 (decode.py:161-166) */
+} ct_head_role;
+
+typedef struct {
+  const float* map;     /* fp32 [B, channels, H, W] */
+  int32_t channels;
+  int32_t role;         /* ct_head_role */
+  int32_t rec_offset;   /* float offset inside a record where the raw gathered row is written */
+} ct_decode_head;
+
+typedef struct {
+  int32_t B, C, H, W, K;
+  const float* hm;          /* post-sigmoid fp32 [B,C,H,W] */
+  int32_t n_heads;
+  ct_decode_head heads[CT_DECODE_MAX_HEADS];
+  /* pose refinement (decode.py:11-81); hm_hp == NULL disables */
+  const float* hm_hp;       /* post-sigmoid [B,J,H,W] */
+  const float* hp_offset;   /* [B,2,H,W] or NULL (then `reg` head map is used if present, else +0.5) */
+  int32_t J;
+  int32_t rec_hps;          /* float offset of the 2J refined keypoints, -1 if none */
+  int32_t rec_kps_score;    /* float offset of kps_score, -1 if none */
+  /* record layout: [score, cls, xs0, ys0, bbox l,t,r,b, ind (int32 bits), ... heads ...] */
+  int32_t rec_floats;       /* floats per record (F) */
+  int32_t has_bbox;
+  float*  records;          /* out [B, K, F] */
+  /* workspace: ct_decode_workspace_bytes(...) bytes, 256B aligned; contents need no init
+   * except that the first 4*B bytes (per-batch arrival counters) are zeroed by the caller
+   * once; the kernel resets them. */
+  void* workspace;
+} ct_decode_desc;
+
+#define CT_REC_SCORE 0
+#define CT_REC_CLS 1
+#define CT_REC_XS 2
+#define CT_REC_YS 3
+#define CT_REC_BBOX 4
+#define CT_REC_IND 8
+#define CT_REC_HEADS 9
+
+int64_t ct_decode_workspace_bytes(int32_t B, int32_t C, int32_t J, int32_t K);
+int ct_decode(const ct_decode_desc* d, void* stream);
+
+/* Gaussian splat of the previous frame's tracks into pre_hm (fp32 [B,1,H,W], zeroed here).
+ * boxes: fp32 [n,5] rows (b, cx_int, cy_int, radius, unused) already in INPUT-resolution
+ * pixel units -- the affine + gaussian_radius arithmetic stays on the host
+ * (detector.py:264-276); the np.maximum splat of image.py:138-154 runs on the device. */
+int ct_render_pre_hm(const float* boxes, int32_t n, float* pre_hm, int32_t B, int32_t H, int32_t W,
+                     void* stream);
+
+/* ---- misc --------------------------------------------------------------------------- */
+const char* ct_last_error(void);
+int ct_abi_version(void);
+/* Kernels launched by this library on the calling thread since the last reset. */
+int64_t ct_launch_count(void);
+void ct_reset_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTB200_H_ */

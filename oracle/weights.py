@@ -1,0 +1,91 @@
+"""TEST INFRASTRUCTURE ONLY.  Deterministic, reference-free synthetic weights.
+
+The reference's default init collapses the 64-channel feature to ~1e-5 (SURVEY hazard H3), and no
+pretrained checkpoint is available offline, so goldens and benchmarks use a variance-preserving
+He-fan-in init that is a pure function of (state-dict key, shape, seed): the SAME tensors can be
+materialised for the reference model (in the build container, to generate goldens) and for the B200
+model (on the GPU box, where /root/reference does not exist).
+"""
+import math
+import zlib
+
+import torch
+
+
+def _gen(key, seed):
+  g = torch.Generator()
+  g.manual_seed((zlib.crc32(key.encode()) ^ (seed * 2654435761)) & 0x7FFFFFFF)
+  return g
+
+
+def make_state_dict(template, seed=317, hm_scale=0.25):
+  """template: {key: tensor} (only shapes/dtypes are read).  Returns a new state_dict."""
+  out = {}
+  bn_prefixes = {k[:-len('.running_mean')] for k in template if k.endswith('.running_mean')}
+  for k, t in template.items():
+    g = _gen(k, seed)
+    shape = tuple(t.shape)
+    if k.endswith('num_batches_tracked'):
+      out[k] = torch.zeros(shape, dtype=t.dtype)
+    elif k.endswith('running_var'):
+      out[k] = torch.empty(shape).uniform_(0.8, 1.2, generator=g)
+    elif k.endswith('running_mean'):
+      out[k] = torch.empty(shape).normal_(0, 0.05, generator=g)
+    elif k.rsplit('.', 1)[0] in bn_prefixes:
+      # BatchNorm affine
+      if k.endswith('weight'):
+        out[k] = torch.empty(shape).uniform_(0.8, 1.2, generator=g)
+      else:
+        out[k] = torch.empty(shape).normal_(0, 0.05, generator=g)
+    elif 'conv_offset_mask' in k:
+      if k.endswith('weight'):
+        out[k] = torch.empty(shape).normal_(0, 0.01, generator=g)
+      else:
+        out[k] = torch.empty(shape).normal_(0, 0.1, generator=g)
+    elif '.up_' in k and k.endswith('weight'):
+      # learnable depthwise upsampling kernel: bilinear +- 10 % so learnability is exercised
+      kk = shape[2]
+      f = (kk + 1) // 2
+      c = (2 * f - 1 - f % 2) / (2. * f)
+      i = torch.arange(kk, dtype=torch.float32)
+      b = 1 - (i / f - c).abs()
+      base = (b[:, None] * b[None, :]).expand(shape)
+      out[k] = base * torch.empty(shape).uniform_(0.9, 1.1, generator=g)
+    elif len(shape) == 4:
+      fan_in = shape[1] * shape[2] * shape[3]
+      w = torch.empty(shape).normal_(0, math.sqrt(2.0 / fan_in), generator=g)
+      head = k.split('.')[0]
+      if 'hm' in head and k.endswith('.2.weight'):
+        w = w * hm_scale
+      out[k] = w
+    elif len(shape) == 1:
+      head = k.split('.')[0]
+      if 'hm' in head and (k.endswith('.2.bias') or k == head + '.bias'):
+        out[k] = torch.full(shape, -4.6)
+      elif k.endswith('.conv.bias'):          # DCN bias
+        out[k] = torch.empty(shape).normal_(0, 0.05, generator=g)
+      else:
+        out[k] = torch.empty(shape).normal_(0, 0.1, generator=g)
+    else:
+      out[k] = torch.zeros(shape, dtype=t.dtype)
+    out[k] = out[k].to(t.dtype) if t.dtype.is_floating_point else out[k]
+  return out
+
+
+def synthetic_inputs(B, H, W, seed=317, n_blobs=20):
+  """images, pre_images ~ N(0,1); pre_hm = max-splat of gaussians."""
+  g = torch.Generator().manual_seed(seed)
+  img = torch.randn(B, 3, H, W, generator=g)
+  pre = torch.randn(B, 3, H, W, generator=g)
+  hm = torch.zeros(B, 1, H, W)
+  ys = torch.arange(H, dtype=torch.float32).view(H, 1)
+  xs = torch.arange(W, dtype=torch.float32).view(1, W)
+  for b in range(B):
+    for _ in range(n_blobs):
+      cx = float(torch.rand(1, generator=g)) * W
+      cy = float(torch.rand(1, generator=g)) * H
+      r = 3 + float(torch.rand(1, generator=g)) * 12
+      sig = (2 * r + 1) / 6
+      blob = torch.exp(-((xs - cx) ** 2 + (ys - cy) ** 2) / (2 * sig * sig))
+      hm[b, 0] = torch.maximum(hm[b, 0], blob)
+  return img, pre, hm

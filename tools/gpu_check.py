@@ -1,0 +1,324 @@
+"""Developer bring-up script (GPU box): python tools/gpu_check.py <section>
+sections: decode | conv_simt | conv_tc | dcn | net_fp32 | net_bf16 | time
+Each section runs in its own process (tools/gpu_check.sh) so a trap in one kernel cannot mask others."""
+import ctypes as C
+import os
+import sys
+import time
+import traceback
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+
+from centertrack_b200 import _lib as L   # noqa
+import ct_oracle as co                    # noqa
+import weights as wt                      # noqa
+
+dev = torch.device('cuda')
+
+
+def stat(name, got, ref, tol):
+  got, ref = got.float().cpu(), ref.float().cpu()
+  err = (got - ref).abs().max().item()
+  rel = err / max(ref.abs().max().item(), 1e-12)
+  ok = err <= tol * max(1.0, ref.abs().max().item())
+  print('%-44s max_abs_err %.3e  rel %.3e  ref_max %.3e  %s' % (name, err, rel, ref.abs().max().item(),
+                                                              'OK' if ok else 'FAIL'))
+  return ok
+
+
+# ------------------------------------------------------------------------------------------
+def run_conv(engine, dtype, x_nchw, w, bias, stride, relu=True, residual=None, a_mode=L.CT_A_CONV, om=None,
+             out_mode=L.CT_OUT_NHWC, n_tile=0, head_act=0, sig_from=1 << 30, ld_pad=0, ch_off=0):
+  lib = L.lib()
+  B, Cin, H, W = x_nchw.shape
+  O, _, k, _ = w.shape
+  act = torch.bfloat16 if dtype == L.CT_BF16 else torch.float32
+  ld_in = Cin + ld_pad
+  xb = torch.zeros((B, H, W, ld_in), dtype=act, device=dev)
+  xb[..., ch_off:ch_off + Cin] = x_nchw.permute(0, 2, 3, 1).to(act)
+  pad = k // 2
+  OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+  if engine == L.CT_ENGINE_TCGEN05 and n_tile == 0:
+    n_tile = min(256, (O + 15) // 16 * 16)
+  nbytes = lib.ct_packed_weight_bytes(engine, O, Cin, k, k, n_tile)
+  wp = torch.empty(nbytes, dtype=torch.uint8)
+  w32 = w.float().contiguous()
+  L.check(lib.ct_pack_weights(engine, C.c_void_p(w32.data_ptr()), O, Cin, k, k, n_tile, C.c_void_p(wp.data_ptr())))
+  wp = wp.to(dev)
+  sh = bias.float().contiguous().to(dev)
+  d = L.ConvDesc()
+  d.engine, d.dtype, d.a_mode = engine, dtype, a_mode
+  d.B, d.H, d.W, d.C_in, d.ld_in, d.C_out = B, H, W, Cin, ld_in, O
+  d.KH = d.KW = k
+  d.stride, d.pad, d.OH, d.OW = stride, pad, OH, OW
+  d.out_mode, d.relu, d.head_act, d.sig_from, d.depth_scale, d.n_tile = out_mode, int(relu), head_act, sig_from, 1.0, n_tile
+  d.x = xb.data_ptr() + ch_off * xb.element_size()
+  d.w, d.shift = wp.data_ptr(), sh.data_ptr()
+  if residual is not None:
+    rb = residual.permute(0, 2, 3, 1).contiguous().to(act).to(dev)
+    d.residual, d.ld_res = rb.data_ptr(), O
+  if om is not None:
+    d.om, d.ld_om = om.data_ptr(), om.shape[-1]
+  if out_mode == L.CT_OUT_NCHW_F32:
+    out = torch.zeros((B, O, OH, OW), dtype=torch.float32, device=dev)
+    d.out, d.ld_out = out.data_ptr(), 0
+  elif out_mode == L.CT_OUT_NHWC_F32:
+    out = torch.zeros((B, OH, OW, 32), dtype=torch.float32, device=dev)
+    d.out, d.ld_out = out.data_ptr(), 32
+  else:
+    out = torch.zeros((B, OH, OW, O), dtype=act, device=dev)
+    d.out, d.ld_out = out.data_ptr(), O
+  L.check(lib.ct_conv_forward(C.byref(d), L.stream_ptr()), 'conv')
+  torch.cuda.synchronize()
+  if out_mode == L.CT_OUT_NCHW_F32:
+    return out
+  return out.permute(0, 3, 1, 2).float()
+
+
+def conv_cases():
+  # (name, B, Cin, Cout, H, W, k, stride, residual, ld_pad, ch_off)
+  return [
+      ('3x3 s1 64->64', 2, 64, 64, 24, 40, 3, 1, True, 0, 0),
+      ('3x3 s2 32->64', 1, 32, 64, 32, 48, 3, 2, False, 0, 0),
+      ('3x3 s1 16->16 (4 taps/slice)', 1, 16, 16, 40, 56, 3, 1, False, 0, 0),
+      ('3x3 s2 16->32', 1, 16, 32, 40, 56, 3, 2, False, 0, 0),
+      ('1x1 448->128 slice of concat', 1, 448, 128, 16, 24, 1, 1, False, 64, 32),
+      ('3x3 s1 256->512 (2 n-tiles)', 1, 256, 512, 8, 12, 3, 1, True, 0, 0),
+      ('3x3 s1 64->1024 (heads.0)', 1, 64, 1024, 16, 24, 3, 1, False, 0, 0),
+  ]
+
+
+def sec_conv(engine, dtype, tol):
+  g = torch.Generator().manual_seed(0)
+  ok = True
+  for (name, B, Cin, Cout, H, W, k, s, res, ld_pad, ch_off) in conv_cases():
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) * (2.0 / (Cin * k * k)) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    OH, OW = (H + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
+    r = torch.randn(B, Cout, OH, OW, generator=g) if res else None
+    if dtype == L.CT_BF16:
+      xq, rq = x.bfloat16().float(), (r.bfloat16().float() if res else None)
+      wq = w.bfloat16().float() if engine == L.CT_ENGINE_TCGEN05 else w
+    else:
+      xq, rq, wq = x, r, w
+    ref = F.conv2d(xq, wq, b, s, k // 2)
+    if res:
+      ref = ref + rq
+    ref = F.relu(ref)
+    try:
+      got = run_conv(engine, dtype, x.to(dev), w, b, s, True, r.to(dev) if res else None, ld_pad=ld_pad, ch_off=ch_off)
+      ok &= stat(name, got, ref, tol)
+    except Exception:
+      traceback.print_exc()
+      ok = False
+  # head-style NCHW fp32 output with sigmoid, C_out=2 / 80
+  for Cout, act in ((2, 0), (80, 1), (1, 2)):
+    x = torch.randn(1, 256, 16, 24, generator=g)
+    w = torch.randn(Cout, 256, 1, 1, generator=g) * 0.05
+    b = torch.randn(Cout, generator=g)
+    xq = x.bfloat16().float() if dtype == L.CT_BF16 else x
+    wq = w.bfloat16().float() if engine == L.CT_ENGINE_TCGEN05 else w
+    ref = F.conv2d(xq, wq, b)
+    if act == 1:
+      ref = torch.sigmoid(ref)
+    if act == 2:
+      ref = 1. / (torch.sigmoid(ref) + 1e-6) - 1.
+    try:
+      got = run_conv(engine, dtype, x.to(dev), w, b, 1, False, out_mode=L.CT_OUT_NCHW_F32, head_act=act)
+      ok &= stat('1x1 256->%d NCHW f32 act%d' % (Cout, act), got, ref, tol * (10 if act == 2 else 1))
+    except Exception:
+      traceback.print_exc()
+      ok = False
+  return ok
+
+
+def sec_dcn(engine, dtype, tol):
+  g = torch.Generator().manual_seed(1)
+  ok = True
+  for (B, Cin, Cout, H, W) in ((1, 64, 64, 24, 40), (2, 128, 64, 16, 16), (1, 256, 256, 8, 12), (1, 512, 256, 4, 6)):
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (Cin * 9)) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    wo = torch.randn(27, Cin, 3, 3, generator=g) * 0.02
+    bo = torch.randn(27, generator=g) * 0.3
+    xq = x.bfloat16().float() if dtype == L.CT_BF16 else x
+    tc = engine == L.CT_ENGINE_TCGEN05
+    wq, woq = (w.bfloat16().float(), wo.bfloat16().float()) if tc else (w, wo)
+    om_ref = F.conv2d(xq, woq, bo, 1, 1)
+    try:
+      om = run_conv(engine, dtype, x.to(dev), wo, bo, 1, relu=False, out_mode=L.CT_OUT_NHWC_F32, sig_from=18, n_tile=32)
+      om_ref_s = om_ref.clone()
+      om_ref_s[:, 18:] = torch.sigmoid(om_ref[:, 18:27])
+      ok &= stat('DCN offset conv %d->27 %dx%d' % (Cin, H, W), om[:, :27], om_ref_s, tol)
+      # main: feed the DEVICE offsets to both sides so sampling positions are identical
+      om_dev = om.permute(0, 2, 3, 1).contiguous()            # [B,H,W,32] fp32
+      om_cpu = om.cpu()
+      cols = co.dcn_sample_columns(xq, om_cpu[:, :18], om_cpu[:, 18:27])
+      if tc:
+        cols = cols.bfloat16().float()
+      ref = torch.einsum('ok,bkp->bop', wq.reshape(Cout, Cin * 9), cols.reshape(B, Cin * 9, H * W)).view(B, Cout, H, W)
+      ref = F.relu(ref + b.view(1, -1, 1, 1))
+      got = run_conv(engine, dtype, x.to(dev), w, b, 1, relu=True, a_mode=L.CT_A_DCN, om=om_dev)
+      ok &= stat('DCN main %d->%d %dx%d' % (Cin, Cout, H, W), got, ref, tol)
+    except Exception:
+      traceback.print_exc()
+      ok = False
+  return ok
+
+
+def sec_decode():
+  from centertrack_b200.decode import generic_decode
+  ok = True
+  rng = np.random.RandomState(7)
+  cases = [(1, 80, 128, 128, 100, 'coco'), (2, 1, 136, 240, 100, 'mot'), (1, 10, 112, 200, 100, 'ddd'),
+           (1, 1, 128, 128, 100, 'pose'), (3, 5, 32, 32, 40, 'ties'), (1, 3, 8, 8, 64, 'tiny')]
+  for (B, Cc, H, W, K, kind) in cases:
+    hm = 1. / (1. + np.exp(-(2 * rng.randn(B, Cc, H, W) - 4.6)))
+    hm = hm.astype(np.float32)
+    if kind == 'ties':
+      hm = np.round(hm * 50) / 50        # massive value ties + plateaus
+      hm = hm.astype(np.float32)
+    out = {'hm': hm, 'reg': rng.randn(B, 2, H, W).astype(np.float32), 'wh': (rng.randn(B, 2, H, W) * 5).astype(np.float32),
+           'tracking': rng.randn(B, 2, H, W).astype(np.float32)}
+    if kind == 'ddd':
+      out.update({'dep': rng.rand(B, 1, H, W).astype(np.float32) * 50, 'rot': rng.randn(B, 8, H, W).astype(np.float32),
+                  'dim': rng.randn(B, 3, H, W).astype(np.float32), 'amodel_offset': rng.randn(B, 2, H, W).astype(np.float32)})
+    if kind == 'pose':
+      hp = 1. / (1. + np.exp(-(2 * rng.randn(B, 17, H, W) - 3.0)))
+      out.update({'hps': (rng.randn(B, 34, H, W) * 6).astype(np.float32), 'hm_hp': hp.astype(np.float32),
+                  'hp_offset': rng.rand(B, 2, H, W).astype(np.float32)})
+    if kind == 'mot':
+      out['ltrb_amodal'] = (rng.randn(B, 4, H, W) * 8).astype(np.float32)
+    ref = co.generic_decode(out, K)
+    dout = {k: torch.from_numpy(v).to(dev) for k, v in out.items()}
+    t0 = time.time()
+    got = generic_decode(dout, K=K)
+    torch.cuda.synchronize()
+    inds = got.inds.cpu().numpy()
+    exact = np.array_equal(inds, ref['_inds'].astype(np.int32))
+    print('[decode %s] B%d C%d %dx%d K%d  top-K indices bit-exact: %s' % (kind, B, Cc, H, W, K, exact))
+    ok &= exact
+    for k in ref:
+      if k.startswith('_'):
+        continue
+      g = got[k].cpu().numpy().reshape(ref[k].shape)
+      tol = 0 if k in ('scores', 'clses', 'xs', 'ys', 'cts', 'bboxes', 'tracking', 'dep', 'rot', 'dim', 'amodel_offset',
+                       'bboxes_amodal') else 1e-5
+      e = np.abs(g - ref[k]).max()
+      good = e <= tol
+      if not good:
+        print('   key %-14s max err %.3e  FAIL' % (k, e))
+      ok &= bool(good)
+    # timing
+    for _ in range(3):
+      generic_decode(dout, K=K)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+      generic_decode(dout, K=K)
+    e1.record()
+    torch.cuda.synchronize()
+    print('   decode latency (incl. python launch overhead): %.1f us' % (e0.elapsed_time(e1) * 1000 / 20))
+  return ok
+
+
+def build_models(cfg_heads, H, W, B=1, seed=317):
+  from centertrack_b200.model import create_model
+  from centertrack_b200.opts import opts
+  task = {'coco_tracking': 'tracking', 'nuscenes_ddd': 'tracking,ddd', 'coco_pose': 'tracking,multi_pose'}[cfg_heads]
+  opt = opts().init([task, '--pre_hm'])
+  m = create_model(opt.arch, opt.heads, opt.head_conv, opt=opt)
+  sd = wt.make_state_dict(m.state_dict(), seed)
+  m.load_state_dict(sd)
+  return opt, m, sd
+
+
+def sec_net(precision, tol, cfg='coco_tracking', H=64, W=96):
+  opt, m, sd = build_models(cfg, H, W)
+  img, pre, hm = wt.synthetic_inputs(1, H, W)
+  trace = {}
+  ref = co.DLA34Oracle(sd, opt.heads).forward(img, pre, hm, trace=trace)
+  m = m.to(dev)
+  eng = m.engine_for(1, H, W, dev, precision)
+  out = eng.forward(img.to(dev), pre.to(dev), hm.to(dev))
+  torch.cuda.synchronize()
+  ok = True
+  for name in ['stem', 'base.level0', 'base.level1', 'base.level2', 'base.level3', 'base.level4', 'base.level5',
+               'dla_up.ida_0.proj_1', 'dla_up.ida_0.node_1', 'dla_up.ida_1.node_2', 'dla_up.ida_2.node_3',
+               'ida_up.node_1', 'feat']:
+    if name in trace and name in eng.named:
+      ok &= stat('[%s] %s' % (precision, name), eng.stage(name), trace[name], tol)
+  for h in opt.heads:
+    ok &= stat('[%s] head %s' % (precision, h), out[h], ref[h], tol)
+  # graph replay == eager
+  eng.in_img.copy_(img.to(dev)); eng.in_pre.copy_(pre.to(dev)); eng.in_hm.copy_(hm.to(dev))
+  eager = {h: out[h].clone() for h in out}
+  rep = eng.replay()
+  torch.cuda.synchronize()
+  same = all(torch.equal(eager[h], rep[h]) for h in eager)
+  print('graph replay bit-identical to eager:', same)
+  return ok and same
+
+
+def sec_time():
+  from centertrack_b200.decode import generic_decode
+  for precision in ('bf16', 'fp32'):
+    for B in ((1, 8, 16) if precision == 'bf16' else (1,)):
+      H = W = 512
+      opt, m, sd = build_models('coco_tracking', H, W)
+      m = m.to(dev)
+      eng = m.engine_for(B, H, W, dev, precision)
+      eng.set_fused_activations(True)
+      img, pre, hm = wt.synthetic_inputs(1, H, W)
+      eng.in_img.copy_(img.to(dev).expand(B, -1, -1, -1)); eng.in_pre.copy_(pre.to(dev).expand(B, -1, -1, -1))
+      eng.in_hm.copy_(hm.to(dev).expand(B, -1, -1, -1))
+      eng.replay()
+      torch.cuda.synchronize()
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      n = 20 if precision == 'bf16' else 3
+      e0.record()
+      for _ in range(n):
+        eng.replay()
+      e1.record()
+      torch.cuda.synchronize()
+      ms = e0.elapsed_time(e1) / n
+      print('[time] %s B=%d 512x512: %.3f ms/step  %.1f frames/s  (%d launches/step)' % (precision, B, ms, B * 1000 / ms, eng.n_launches))
+      if precision == 'bf16' and B == 1:
+        # per-op eager timing
+        torch.cuda.synchronize()
+        times = []
+        for kind, pl, name in eng.ops:
+          pass
+      del eng, m
+      torch.cuda.empty_cache()
+  return True
+
+
+if __name__ == '__main__':
+  sec = sys.argv[1]
+  t0 = time.time()
+  print('==== section %s on %s' % (sec, torch.cuda.get_device_name(0)))
+  if sec == 'decode':
+    ok = sec_decode()
+  elif sec == 'conv_simt':
+    ok = sec_conv(L.CT_ENGINE_SIMT, L.CT_F32, 2e-5) & sec_conv(L.CT_ENGINE_SIMT, L.CT_BF16, 6e-3)
+  elif sec == 'conv_tc':
+    ok = sec_conv(L.CT_ENGINE_TCGEN05, L.CT_BF16, 6e-3)
+  elif sec == 'dcn':
+    ok = sec_dcn(L.CT_ENGINE_SIMT, L.CT_F32, 5e-5) & sec_dcn(L.CT_ENGINE_TCGEN05, L.CT_BF16, 8e-3)
+  elif sec == 'net_fp32':
+    ok = sec_net('fp32', 1e-3)
+  elif sec == 'net_bf16':
+    ok = sec_net('bf16', 6e-2)
+  elif sec == 'time':
+    ok = sec_time()
+  print('==== section %s %s (%.1fs)' % (sec, 'PASSED' if ok else 'FAILED', time.time() - t0))
+  sys.exit(0 if ok else 1)
