@@ -1,0 +1,170 @@
+"""TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference, via oracle/ref_harness.py) on CPU in the build container:
+
+    python oracle/gen_golden.py            # needs /root/reference; run here, commit the outputs
+
+Inputs and weights are pure functions of seeds (oracle/weights.py, numpy RandomState) so the GPU box
+regenerates them bit-identically without the reference; only the reference's OUTPUTS are stored.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_harness as rh          # noqa
+import weights as wt              # noqa
+
+OUT = os.path.join(HERE, '..', 'tests', 'golden')
+SMALL_HW = (64, 96)
+STAGES = ['base.level2', 'base.level3', 'base.level4', 'base.level5', 'dla_up.ida_0.proj_1',
+          'dla_up.ida_0.node_1', 'dla_up.ida_1.node_2', 'dla_up.ida_2.node_3', 'ida_up.node_1', 'ida_up.node_2']
+
+
+def decode_inputs(kind, B, C, H, W, seed):
+  """Seeded decode-only inputs: hm = sigmoid(2 N(0,1) - 4.6), heads ~ N(0,1)."""
+  rng = np.random.RandomState(seed)
+  out = {'hm': (1. / (1. + np.exp(-(2 * rng.randn(B, C, H, W) - 4.6)))).astype(np.float32),
+         'reg': rng.rand(B, 2, H, W).astype(np.float32),
+         'wh': (rng.randn(B, 2, H, W) * 6).astype(np.float32),
+         'tracking': (rng.randn(B, 2, H, W) * 3).astype(np.float32)}
+  if kind == 'ddd':
+    out.update({'dep': (rng.rand(B, 1, H, W) * 60).astype(np.float32),
+                'rot': rng.randn(B, 8, H, W).astype(np.float32),
+                'dim': (rng.rand(B, 3, H, W) * 4).astype(np.float32),
+                'amodel_offset': rng.randn(B, 2, H, W).astype(np.float32)})
+  if kind == 'pose':
+    out.update({'hps': (rng.randn(B, 34, H, W) * 6).astype(np.float32),
+                'hm_hp': (1. / (1. + np.exp(-(2 * rng.randn(B, 17, H, W) - 3.0)))).astype(np.float32),
+                'hp_offset': rng.rand(B, 2, H, W).astype(np.float32)})
+  if kind == 'mot':
+    out['ltrb_amodal'] = (rng.randn(B, 4, H, W) * 8).astype(np.float32)
+  return out
+
+
+DECODE_CASES = [('coco', 1, 80, 128, 128, 100, 11), ('mot', 1, 1, 136, 240, 100, 12),
+                ('ddd', 1, 10, 112, 200, 100, 13), ('pose', 1, 1, 128, 128, 100, 14),
+                ('coco', 2, 80, 32, 32, 50, 15)]
+
+
+def gen_net():
+  for cfg in ['coco_tracking', 'mot', 'nuscenes_ddd', 'coco_pose']:
+    opt, model = rh.build_reference_model(cfg, input_hw=SMALL_HW)
+    sd = wt.make_state_dict(model.state_dict(), 317)
+    model.load_state_dict(sd)
+    img, pre, hm = wt.synthetic_inputs(1, *SMALL_HW)
+    acts = {}
+    hooks = []
+    if cfg == 'coco_tracking':
+      mods = dict(model.named_modules())
+      for name in STAGES:
+        hooks.append(mods[name].register_forward_hook(
+            lambda m, i, o, name=name: acts.__setitem__(name, o.detach().clone())))
+    with torch.no_grad():
+      out = model(img, pre, hm)[-1]
+    for h in hooks:
+      h.remove()
+    data = {'head.' + k: v.numpy() for k, v in out.items()}
+    data.update({'stage.' + k: v.numpy() for k, v in acts.items()})
+    data['keys'] = np.array(sorted(sd.keys()))
+    np.savez_compressed(os.path.join(OUT, 'net_%s_64x96.npz' % cfg), **data)
+    print('net', cfg, {k: v.shape for k, v in data.items() if k != 'keys'})
+
+
+def gen_e2e():
+  """coco_tracking 512x512 through the reference model + _sigmoid_output + generic_decode."""
+  from model.decode import generic_decode
+  opt, model = rh.build_reference_model('coco_tracking')
+  sd = wt.make_state_dict(model.state_dict(), 317)
+  model.load_state_dict(sd)
+  img, pre, hm = wt.synthetic_inputs(1, 512, 512)
+  with torch.no_grad():
+    out = model(img, pre, hm)[-1]
+    out['hm'] = out['hm'].sigmoid_()
+    out['pre_inds'] = None
+    dets = generic_decode({k: (v.clone() if v is not None else None) for k, v in out.items()}, K=100, opt=opt)
+  rng = np.random.RandomState(3)
+  pos = rng.randint(0, 128 * 128, size=512)
+  data = {'pos': pos}
+  for k in ('hm', 'reg', 'wh', 'tracking'):
+    v = out[k].numpy().reshape(out[k].shape[1], -1)
+    data['sample.' + k] = v[:, pos]
+  data.update({'det.' + k: v.numpy() for k, v in dets.items()})
+  hmn = out['hm'].numpy()
+  data['hm_max_per_class'] = hmn.reshape(80, -1).max(1)
+  np.savez_compressed(os.path.join(OUT, 'e2e_coco_tracking_512.npz'), **data)
+  print('e2e', {k: v.shape for k, v in data.items()})
+
+
+def gen_decode():
+  from model.decode import generic_decode
+  data = {}
+  for i, (kind, B, C, H, W, K, seed) in enumerate(DECODE_CASES):
+    inp = decode_inputs(kind, B, C, H, W, seed)
+    opt = rh.make_opt('coco_tracking')
+    t = {k: torch.from_numpy(v.copy()) for k, v in inp.items()}
+    t['pre_inds'] = None
+    with torch.no_grad():
+      dets = generic_decode(t, K=K, opt=opt)
+    for k, v in dets.items():
+      data['%d.%s' % (i, k)] = v.numpy()
+  np.savez_compressed(os.path.join(OUT, 'decode_cases.npz'), **data)
+  print('decode', len(data), 'arrays')
+
+
+def gen_post_track():
+  """3 synthetic frames through the reference's generic_post_process + Tracker (greedy)."""
+  from utils.post_process import generic_post_process
+  from utils.tracker import Tracker
+  from utils.image import get_affine_transform
+  from model.decode import generic_decode
+  data = {}
+  for ci, (cfg, kind, C, H, W) in enumerate([('coco_tracking', 'coco', 80, 128, 128),
+                                             ('nuscenes_ddd', 'ddd', 10, 112, 200),
+                                             ('coco_pose', 'pose', 1, 128, 128)]):
+    opt = rh.make_opt(cfg, extra=['--track_thresh', '0.05', '--new_thresh', '0.05'])
+    tracker = Tracker(opt)
+    height, width = 480, 640
+    c = np.array([width / 2., height / 2.], dtype=np.float32)
+    s = max(height, width) * 1.0
+    calib = np.array([[1200, 0, width / 2, 0], [0, 1200, height / 2, 0], [0, 0, 1, 0]], dtype=np.float32)
+    base = decode_inputs(kind, 1, C, H, W, 100 + ci)
+    for frame in range(3):
+      inp = {k: v.copy() for k, v in base.items()}
+      rng = np.random.RandomState(1000 + frame)
+      inp['tracking'] = (rng.randn(*inp['tracking'].shape) * 0.5).astype(np.float32)
+      if 'dep' in inp:
+        inp['dep'] = (1. / (1. / (1 + np.exp(-inp['dep'] / 30 + 1)) + 1e-6) - 1.).astype(np.float32)
+      t = {k: torch.from_numpy(v) for k, v in inp.items()}
+      t['pre_inds'] = None
+      with torch.no_grad():
+        dets = generic_decode(t, K=100, opt=opt)
+      dets = {k: v.numpy() for k, v in dets.items()}
+      res = generic_post_process(opt, dets, [c], [s], H, W, opt.num_classes, [calib], height, width)[0]
+      res = [r for r in res if r['score'] > opt.out_thresh]
+      if frame == 0:
+        tracker.init_track([])
+      out = tracker.step(res)
+      for key in out[0].keys():
+        arr = np.array([np.asarray(o[key], dtype=np.float64) for o in out])
+        data['%s.f%d.%s' % (cfg, frame, key)] = arr
+      data['%s.f%d.n' % (cfg, frame)] = np.array([len(out), tracker.id_count])
+  np.savez_compressed(os.path.join(OUT, 'post_track.npz'), **data)
+  print('post_track', len(data), 'arrays')
+
+
+if __name__ == '__main__':
+  os.makedirs(OUT, exist_ok=True)
+  torch.manual_seed(0)
+  which = sys.argv[1:] or ['net', 'e2e', 'decode', 'post']
+  rh.install()
+  if 'net' in which:
+    gen_net()
+  if 'decode' in which:
+    gen_decode()
+  if 'post' in which:
+    gen_post_track()
+  if 'e2e' in which:
+    gen_e2e()

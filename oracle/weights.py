@@ -18,8 +18,39 @@ def _gen(key, seed):
   return g
 
 
-def make_state_dict(template, seed=317, hm_scale=0.25):
-  """template: {key: tensor} (only shapes/dtypes are read).  Returns a new state_dict."""
+_cache = {}
+
+
+def make_state_dict(template, seed=317, hm_scale=0.25, calibrate=True):
+  """template: {key: tensor} (only shapes/dtypes are read).  Returns a new state_dict.
+
+  calibrate=True additionally sets every BatchNorm's running_mean/var to the statistics of its input
+  on one synthetic 128x160 frame pair (what training-mode BN would have accumulated), so activations
+  stay O(1) through the 50-layer trunk and DCN offsets are O(1 px) like in a trained network.  Without
+  it the residual stream grows to |x|~250 and offsets to tens of pixels -- an ill-conditioned network
+  on which no reduced-precision implementation can be judged."""
+  ck = (tuple(sorted((k, tuple(v.shape)) for k, v in template.items())), seed, hm_scale, calibrate)
+  if ck in _cache:
+    return {k: v.clone() for k, v in _cache[ck].items()}
+  out = _raw_state_dict(template, seed, hm_scale)
+  if calibrate:
+    import ct_oracle as co
+    heads = {k.split('.')[0]: 1 for k in out
+             if not k.startswith(('base.', 'dla_up.', 'ida_up.'))}
+    orc = co.DLA34Oracle(out, heads)
+    orc.calibrate = True
+    img, pre, hm = synthetic_inputs(1, 128, 160, seed=seed + 1)
+    has_pre = 'base.pre_img_layer.0.weight' in out
+    has_hm = 'base.pre_hm_layer.0.weight' in out
+    orc.feats(img, pre if has_pre else None, hm if has_hm else None)
+    for k in out:
+      if k.endswith('running_mean') or k.endswith('running_var'):
+        out[k] = orc.sd[k].to(out[k].dtype).clone()
+  _cache[ck] = {k: v.clone() for k, v in out.items()}
+  return out
+
+
+def _raw_state_dict(template, seed, hm_scale):
   out = {}
   bn_prefixes = {k[:-len('.running_mean')] for k in template if k.endswith('.running_mean')}
   for k, t in template.items():

@@ -1,0 +1,81 @@
+"""The C-ABI library builds for sm_100a, loads without a GPU, and exports every symbol the public
+header declares (no compute calls here)."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+
+
+def _declared():
+  src = open(os.path.join(ROOT, 'include', 'ctb200.h')).read()
+  src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+  return sorted(set(re.findall(r'\b(ct_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_header_declares_entry_points():
+  names = _declared()
+  for must in ('ct_conv_forward', 'ct_decode', 'ct_stem_forward', 'ct_maxpool2', 'ct_upsample_add',
+               'ct_pack_weights', 'ct_last_error'):
+    assert must in names
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+  lib = ctypes.CDLL(built_lib)
+  for name in _declared():
+    assert hasattr(lib, name), 'libctb200.so does not export %s' % name
+  lib.ct_abi_version.restype = ctypes.c_int
+  assert lib.ct_abi_version() == 1
+
+
+def test_python_binding_lists_match_header(built_lib):
+  from centertrack_b200 import _lib
+  assert sorted(_lib.EXPORTS) == _declared()
+  _lib.lib()     # argtypes/restype wiring must not raise
+
+
+def test_sass_is_blackwell_native(built_lib):
+  """tcgen05.mma / tcgen05.ld / TMA bulk copy must be in the SASS (UTCHMMA / LDTM / UBLKCP)."""
+  import shutil
+  import subprocess
+  if shutil.which('cuobjdump') is None:
+    import pytest
+    pytest.skip('cuobjdump not available')
+  sass = subprocess.run(['cuobjdump', '-sass', built_lib], capture_output=True, text=True).stdout
+  for mnemonic in ('UTCHMMA', 'LDTM', 'UBLKCP'):
+    assert mnemonic in sass, mnemonic
+
+
+def test_host_weight_packing_roundtrip(built_lib):
+  """ct_pack_weights (host code, no GPU): SIMT layout k-major; tcgen05 layout = 128B-swizzled tiles."""
+  import numpy as np
+  from centertrack_b200 import _lib as L
+  lib = L.lib()
+  rng = np.random.RandomState(0)
+  O, I, k = 24, 16, 3
+  w = rng.randn(O, I, k, k).astype(np.float32)
+  n = lib.ct_packed_weight_bytes(L.CT_ENGINE_SIMT, O, I, k, k, 0)
+  dst = np.zeros(n // 4, dtype=np.float32)
+  assert lib.ct_pack_weights(L.CT_ENGINE_SIMT, w.ctypes.data, O, I, k, k, 0, dst.ctypes.data) == 0
+  ldw = 64
+  ref = np.zeros((k * k * I, ldw), np.float32)
+  ref[:, :O] = w.transpose(2, 3, 1, 0).reshape(k * k * I, O)
+  assert np.array_equal(dst.reshape(-1, ldw), ref)
+  # tcgen05: de-swizzle and compare against bf16-rounded weights
+  n_tile = 32
+  n = lib.ct_packed_weight_bytes(L.CT_ENGINE_TCGEN05, O, I, k, k, n_tile)
+  ks = (k * k * I + 63) // 64
+  assert n == 1 * ks * n_tile * 64 * 2
+  dst = np.zeros(n // 2, dtype=np.uint16)
+  assert lib.ct_pack_weights(L.CT_ENGINE_TCGEN05, w.ctypes.data, O, I, k, k, n_tile, dst.ctypes.data) == 0
+  tiles = dst.reshape(ks, n_tile, 8, 8)          # [slice][row][chunk][elem]
+  wk = w.transpose(0, 2, 3, 1).reshape(O, k * k * I)   # k = tap*C_in + c
+  import torch
+  wk_bf16 = torch.from_numpy(wk).bfloat16().view(torch.int16).numpy().view(np.uint16)
+  for r in range(O):
+    for kk in range(k * k * I):
+      s, j = divmod(kk, 64)
+      chunk = (j // 8) ^ (r & 7)
+      assert tiles[s, r, chunk, j % 8] == wk_bf16[r, kk]
+  assert lib.ct_pack_weights(L.CT_ENGINE_TCGEN05, w.ctypes.data, O, I, k, k, 20, dst.ctypes.data) != 0
+  assert b'n_tile' in lib.ct_last_error()

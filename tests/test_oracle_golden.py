@@ -1,0 +1,136 @@
+"""The oracle (oracle/ct_oracle.py) is pinned against outputs of the UNMODIFIED reference run in the
+build container (fixtures in tests/golden/, generator oracle/gen_golden.py).  CPU only.
+
+Tolerances: network = 1e-3 absolute (north_star's fp32 bar; observed ~3e-4, two fp32 summation
+orders); decode / top-K indices = bit-exact; post-process / tracker = 1e-4 relative (float32 affine
+arithmetic evaluated in a different association order)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import ct_oracle as co
+import weights as wt
+from helpers import DECODE_CASES, decode_inputs, make_opt, make_model
+
+
+@pytest.mark.parametrize('cfg', ['coco_tracking', 'mot', 'nuscenes_ddd', 'coco_pose'])
+def test_oracle_network_matches_reference_golden(cfg, golden_dir):
+  g = np.load(os.path.join(golden_dir, 'net_%s_64x96.npz' % cfg))
+  opt, model, sd = make_model(cfg)
+  assert sorted(sd.keys()) == list(g['keys'])          # state-dict key compatibility
+  img, pre, hm = wt.synthetic_inputs(1, 64, 96)
+  trace = {}
+  out = co.DLA34Oracle(sd, opt.heads).forward(img, pre, hm, trace=trace)
+  for k in out:
+    ref = g['head.' + k]
+    assert out[k].shape == ref.shape
+    assert np.abs(out[k].numpy() - ref).max() < 1e-3, k
+  for k in [x for x in g.files if x.startswith('stage.')]:
+    name = k[len('stage.'):]
+    key = 'feat' if name == 'ida_up.node_2' else name
+    assert np.abs(trace[key].numpy() - g[k]).max() < 1e-3 * max(1.0, np.abs(g[k]).max()), name
+
+
+@pytest.mark.parametrize('case', range(len(DECODE_CASES)))
+def test_oracle_decode_matches_reference_golden(case, golden_dir):
+  g = np.load(os.path.join(golden_dir, 'decode_cases.npz'))
+  kind, B, C, H, W, K, seed = DECODE_CASES[case]
+  inp = decode_inputs(kind, B, C, H, W, seed)
+  out = co.generic_decode(inp, K)
+  keys = [k.split('.', 1)[1] for k in g.files if k.startswith('%d.' % case)]
+  assert sorted(keys) == sorted(k for k in out if not k.startswith('_'))
+  for k in keys:
+    ref = g['%d.%s' % (case, k)]
+    got = out[k].reshape(ref.shape)
+    if k in ('hps', 'kps_score'):
+      assert np.abs(got - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max()), k
+    else:
+      assert np.array_equal(got, ref), k          # bit-exact (tie-free seeded inputs)
+  # the flat indices are consistent with xs/ys
+  assert np.array_equal(out['_inds'], (out['ys'] * W + out['xs']).astype(np.int64))
+
+
+def _run_post_track(cfg, kind, C, H, W, ci, post_fn, tracker):
+  height, width = 480, 640
+  c = np.array([width / 2., height / 2.], dtype=np.float32)
+  s = max(height, width) * 1.0
+  calib = np.array([[1200, 0, width / 2, 0], [0, 1200, height / 2, 0], [0, 0, 1, 0]], dtype=np.float32)
+  base = decode_inputs(kind, 1, C, H, W, 100 + ci)
+  frames = []
+  for frame in range(3):
+    inp = {k: v.copy() for k, v in base.items()}
+    rng = np.random.RandomState(1000 + frame)
+    inp['tracking'] = (rng.randn(*inp['tracking'].shape) * 0.5).astype(np.float32)
+    if 'dep' in inp:
+      inp['dep'] = (1. / (1. / (1 + np.exp(-inp['dep'] / 30 + 1)) + 1e-6) - 1.).astype(np.float32)
+    dets = co.generic_decode(inp, 100)
+    dets = {k: v for k, v in dets.items() if not k.startswith('_')}
+    res = post_fn(dets, c, s, H, W, calib, height, width)
+    res = [r for r in res if r['score'] > 0.05]
+    if frame == 0:
+      tracker.init_track([])
+    frames.append((tracker.step(res), tracker.id_count))
+  return frames
+
+
+CASES = [('coco_tracking', 'coco', 80, 128, 128), ('nuscenes_ddd', 'ddd', 10, 112, 200),
+         ('coco_pose', 'pose', 1, 128, 128)]
+
+
+def _check_frames(cfg, frames, g):
+  for f, (out, id_count) in enumerate(frames):
+    n = g['%s.f%d.n' % (cfg, f)]
+    assert [len(out), id_count] == list(n)
+    for key in out[0].keys():
+      ref = g['%s.f%d.%s' % (cfg, f, key)]
+      got = np.array([np.asarray(o[key], dtype=np.float64) for o in out])
+      if key in ('tracking_id', 'age', 'active', 'class'):
+        assert np.array_equal(got, ref), (cfg, f, key)
+      else:
+        assert np.allclose(got, ref, rtol=1e-4, atol=1e-3), (cfg, f, key, np.abs(got - ref).max())
+
+
+@pytest.mark.parametrize('ci', range(3))
+def test_oracle_post_process_and_tracker_match_reference_golden(ci, golden_dir):
+  g = np.load(os.path.join(golden_dir, 'post_track.npz'))
+  cfg, kind, C, H, W = CASES[ci]
+  post = lambda d, c, s, h, w, calib, height, width: co.generic_post_process(d, [c], [s], h, w, 0.05, [calib])[0]
+  frames = _run_post_track(cfg, kind, C, H, W, ci, post, co.TrackerOracle(0.05))
+  _check_frames(cfg, frames, g)
+
+
+@pytest.mark.parametrize('ci', range(3))
+def test_product_host_post_process_and_tracker_match_reference_golden(ci, golden_dir):
+  """centertrack_b200.post_process / tracker are host (numpy) code of the product path."""
+  from centertrack_b200.post_process import generic_post_process
+  from centertrack_b200.tracker import Tracker
+  g = np.load(os.path.join(golden_dir, 'post_track.npz'))
+  cfg, kind, C, H, W = CASES[ci]
+  opt = make_opt(cfg, ['--track_thresh', '0.05', '--new_thresh', '0.05'])
+  post = lambda d, c, s, h, w, calib, height, width: generic_post_process(
+      opt, d, [c], [s], h, w, opt.num_classes, [calib], height, width)[0]
+  frames = _run_post_track(cfg, kind, C, H, W, ci, post, Tracker(opt))
+  _check_frames(cfg, frames, g)
+
+
+def test_oracle_dcn_matches_torchvision():
+  """Second, independent anchor for the un-vendored DCNv2 arithmetic."""
+  tv = pytest.importorskip('torchvision.ops')
+  g = torch.Generator().manual_seed(5)
+  x = torch.randn(2, 16, 9, 11, generator=g)
+  w = torch.randn(8, 16, 3, 3, generator=g) * 0.1
+  b = torch.randn(8, generator=g)
+  wo = torch.randn(27, 16, 3, 3, generator=g) * 0.05      # offsets up to a few pixels, some out of image
+  bo = torch.randn(27, generator=g) * 1.5
+  got = co.dcn_v2_forward(x, w, b, wo, bo)
+  om = torch.nn.functional.conv2d(x, wo, bo, 1, 1)
+  ref = tv.deform_conv2d(x, om[:, :18], w, b, 1, 1, 1, torch.sigmoid(om[:, 18:]))
+  assert (got - ref).abs().max() < 1e-4
+
+
+def test_oracle_topk_tie_rule():
+  v = np.array([[0.5, 0.0, 0.5, 0.7, 0.0, 0.0]], dtype=np.float32)
+  s, i = co.topk_desc(v, 4)
+  assert list(i[0]) == [3, 0, 2, 1] and list(s[0]) == [0.7, 0.5, 0.5, 0.0]
