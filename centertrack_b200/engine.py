@@ -368,24 +368,28 @@ class DLA34Engine(object):
     self.fused_act = on
     self.graph = None
 
+  def _run_one(self, kind, pl, name, img_ptr, pre_ptr, hm_ptr, st):
+    lib = self.lib
+    if kind == 'conv':
+      rc = lib.ct_conv_forward(C.byref(pl), st)
+    elif kind == 'stem':
+      rc = lib.ct_stem_forward(img_ptr, pre_ptr, hm_ptr, L.ptr(self.stem_w), L.ptr(self.stem_shift),
+                               C.c_void_p(pl.ptr), self.ct_dtype, self.B, self.H, self.W, pl.ld, st)
+    elif kind == 'pool':
+      x, o = pl
+      rc = lib.ct_maxpool2(C.c_void_p(x.ptr), C.c_void_p(o.ptr), self.ct_dtype, self.B, x.H, x.W, x.C,
+                           x.ld, o.ld, st)
+    else:
+      x, skip, w, o, f = pl
+      rc = lib.ct_upsample_add(C.c_void_p(x.ptr), C.c_void_p(skip.ptr), L.ptr(w), C.c_void_p(o.ptr),
+                               self.ct_dtype, self.B, x.H, x.W, x.C, f, x.ld, skip.ld, o.ld, st)
+    if rc != 0:
+      L.check(rc, '%s (%s)' % (kind, name))
+
   def _run_ops(self, img_ptr, pre_ptr, hm_ptr):
-    lib, st = self.lib, L.stream_ptr()
+    st = L.stream_ptr()
     for kind, pl, name in self.ops:
-      if kind == 'conv':
-        rc = lib.ct_conv_forward(C.byref(pl), st)
-      elif kind == 'stem':
-        rc = lib.ct_stem_forward(img_ptr, pre_ptr, hm_ptr, L.ptr(self.stem_w), L.ptr(self.stem_shift),
-                                 C.c_void_p(pl.ptr), self.ct_dtype, self.B, self.H, self.W, pl.ld, st)
-      elif kind == 'pool':
-        x, o = pl
-        rc = lib.ct_maxpool2(C.c_void_p(x.ptr), C.c_void_p(o.ptr), self.ct_dtype, self.B, x.H, x.W, x.C,
-                             x.ld, o.ld, st)
-      else:
-        x, skip, w, o, f = pl
-        rc = lib.ct_upsample_add(C.c_void_p(x.ptr), C.c_void_p(skip.ptr), L.ptr(w), C.c_void_p(o.ptr),
-                                 self.ct_dtype, self.B, x.H, x.W, x.C, f, x.ld, skip.ld, o.ld, st)
-      if rc != 0:
-        L.check(rc, '%s (%s)' % (kind, name))
+      self._run_one(kind, pl, name, img_ptr, pre_ptr, hm_ptr, st)
 
   @property
   def n_launches(self):

@@ -1,0 +1,134 @@
+"""StreamRunner: the batched, graph-captured form of `Detector.process` for B independent video streams
+on one GPU (streams shard across GPUs, replicas of the weights, no data-path collective).
+
+One step = for every stream its current frame: network (pre_img = that stream's previous frame, kept on
+the device exactly like detector.py:148) + fused sigmoid + fused decode -> one packed record buffer
+[B,K,F].  Two input slots alternate, so step t's images are step t+1's pre_images without a copy, and
+two CUDA graphs (one per slot parity) replay the whole step as a single launch each.
+
+The end-to-end form (`step_host`) takes HOST frames: pinned staging, H2D on a copy stream overlapped
+with the previous step's compute, graph replay, D2H of the records.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .decode import generic_decode
+
+
+class StreamRunner(object):
+
+  def __init__(self, model, B, H, W, K=100, precision='bf16', device='cuda', use_graph=True):
+    self.B, self.H, self.W, self.K = B, H, W, K
+    self.device = torch.device(device)
+    self.model = model
+    self.eng = model.engine_for(B, H, W, self.device, precision)
+    self.eng.set_fused_activations(True)
+    f32 = torch.float32
+    self.img = [torch.zeros((B, 3, H, W), dtype=f32, device=self.device) for _ in range(2)]
+    self.hm = [torch.zeros((B, 1, H, W), dtype=f32, device=self.device) for _ in range(2)]
+    self.h_img = [torch.zeros((B, 3, H, W), dtype=f32).pin_memory() for _ in range(2)]
+    self.h_hm = [torch.zeros((B, 1, H, W), dtype=f32).pin_memory() for _ in range(2)]
+    self.rec = None
+    self.layout = None
+    self.use_graph = use_graph
+    self.graphs = [None, None]
+    self.compute = torch.cuda.Stream(device=self.device)
+    self.copy = torch.cuda.Stream(device=self.device)
+    self.ev_in = [torch.cuda.Event() for _ in range(2)]      # slot uploaded
+    self.ev_done = [torch.cuda.Event() for _ in range(2)]    # slot's step finished (inputs reusable)
+    self.t = 0
+    self._eager(0)                                           # sizes the record buffer
+    torch.cuda.synchronize(self.device)
+    self.h_rec = [torch.zeros_like(self.rec, device='cpu').pin_memory() for _ in range(2)]
+    self.launches_per_step = self.eng.n_launches + 1
+
+  # one step, eager launches on the current stream
+  def _eager(self, slot):
+    out = dict(self.eng.forward(self.img[slot], self.img[1 - slot], self.hm[slot]))
+    res = generic_decode(out, K=self.K, records_out=self.rec)
+    if self.rec is None:
+      self.rec, self.layout = res.records, res.layout
+    return res
+
+  def _graph(self, slot):
+    if self.graphs[slot] is None:
+      s = torch.cuda.Stream(device=self.device)
+      s.wait_stream(torch.cuda.current_stream())
+      with torch.cuda.stream(s):
+        self._eager(slot)
+      torch.cuda.current_stream().wait_stream(s)
+      g = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(g):
+        self._eager(slot)
+      self.graphs[slot] = g
+    return self.graphs[slot]
+
+  def warm(self):
+    for s in (0, 1):
+      if self.use_graph:
+        self._graph(s)
+      else:
+        self._eager(s)
+    torch.cuda.synchronize(self.device)
+
+  def load_device_inputs(self, images, pre_hms, slot):
+    self.img[slot].copy_(images)
+    self.hm[slot].copy_(pre_hms)
+
+  def step_device(self):
+    """Inputs already resident in the slot buffers; runs on the current stream."""
+    slot = self.t & 1
+    if self.use_graph:
+      self._graph(slot).replay()
+    else:
+      self._eager(slot)
+    self.t += 1
+    return self.rec
+
+  def step_host(self, images, pre_hms):
+    """images [B,3,H,W], pre_hms [B,1,H,W]: float32 HOST tensors (what Detector.pre_process /
+    _get_additional_inputs produce).  Returns the records of the PREVIOUS call (None the first time) --
+    a one-step software pipeline: this step's H2D overlaps the previous step's compute."""
+    slot = self.t & 1
+    src_img, src_hm = images, pre_hms
+    if not (images.is_pinned() and pre_hms.is_pinned()):   # pageable input: stage through pinned memory
+      self.h_img[slot].copy_(images)
+      self.h_hm[slot].copy_(pre_hms)
+      src_img, src_hm = self.h_img[slot], self.h_hm[slot]
+    with torch.cuda.stream(self.copy):
+      self.copy.wait_event(self.ev_done[slot])       # slot's old contents no longer needed (as pre_img of t-1)
+      self.img[slot].copy_(src_img, non_blocking=True)
+      self.hm[slot].copy_(src_hm, non_blocking=True)
+      self.ev_in[slot].record(self.copy)
+    prev = self.fetch() if self.t > 0 else None
+    with torch.cuda.stream(self.compute):
+      self.compute.wait_event(self.ev_in[slot])
+      if self.use_graph:
+        self._graph(slot).replay()
+      else:
+        self._eager(slot)
+      self.h_rec[slot].copy_(self.rec, non_blocking=True)
+      # the OTHER slot (this step's pre_images) may be overwritten once this step is done
+      self.ev_done[1 - slot].record(self.compute)
+    self.t += 1
+    return prev
+
+  def fetch(self):
+    """Blocks until the last submitted step finished; returns its records as numpy [B,K,F]."""
+    self.compute.synchronize()
+    return self.h_rec[(self.t - 1) & 1].numpy()
+
+  @property
+  def h2d_bytes_per_step(self):
+    return self.B * 4 * self.H * self.W * 4
+
+  @property
+  def d2h_bytes_per_step(self):
+    return self.rec.numel() * 4
+
+  def views(self, rec_np):
+    from .decode import views_from_records
+    return {k: v.numpy() for k, v in views_from_records(torch.from_numpy(rec_np), self.layout).items()}

@@ -1,11 +1,18 @@
-"""TEST INFRASTRUCTURE ONLY.  Deterministic, reference-free synthetic weights.
+"""Deterministic, reference-free synthetic weights and inputs for benchmarks, smoke and tests.
 
 The reference's default init collapses the 64-channel feature to ~1e-5 (SURVEY hazard H3), and no
 pretrained checkpoint is available offline, so goldens and benchmarks use a variance-preserving
 He-fan-in init that is a pure function of (state-dict key, shape, seed): the SAME tensors can be
 materialised for the reference model (in the build container, to generate goldens) and for the B200
 model (on the GPU box, where /root/reference does not exist).
+
+BatchNorm running statistics come from data/bn_calib_seed<seed>.npz -- the batch statistics each BN
+saw on one synthetic frame pair, recorded once by oracle/calibrate.py (what training-mode BN would have
+accumulated).  With them activations stay O(1) through the 50-layer trunk and DCN offsets are O(1 px)
+like in a trained network; without them the residual stream grows to |x|~250 and offsets to tens of
+pixels, an ill-conditioned network on which no reduced-precision implementation can be judged.
 """
+import os
 import math
 import zlib
 
@@ -19,33 +26,28 @@ def _gen(key, seed):
 
 
 _cache = {}
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data')
 
 
-def make_state_dict(template, seed=317, hm_scale=0.25, calibrate=True):
-  """template: {key: tensor} (only shapes/dtypes are read).  Returns a new state_dict.
+def calib_path(seed):
+  return os.path.join(_DATA, 'bn_calib_seed%d.npz' % seed)
 
-  calibrate=True additionally sets every BatchNorm's running_mean/var to the statistics of its input
-  on one synthetic 128x160 frame pair (what training-mode BN would have accumulated), so activations
-  stay O(1) through the 50-layer trunk and DCN offsets are O(1 px) like in a trained network.  Without
-  it the residual stream grows to |x|~250 and offsets to tens of pixels -- an ill-conditioned network
-  on which no reduced-precision implementation can be judged."""
-  ck = (tuple(sorted((k, tuple(v.shape)) for k, v in template.items())), seed, hm_scale, calibrate)
+
+def make_state_dict(template, seed=317, hm_scale=0.25, calibrated=True):
+  """template: {key: tensor} (only shapes/dtypes are read).  Returns a new state_dict."""
+  ck = (tuple(sorted((k, tuple(v.shape)) for k, v in template.items())), seed, hm_scale, calibrated)
   if ck in _cache:
     return {k: v.clone() for k, v in _cache[ck].items()}
   out = _raw_state_dict(template, seed, hm_scale)
-  if calibrate:
-    import ct_oracle as co
-    heads = {k.split('.')[0]: 1 for k in out
-             if not k.startswith(('base.', 'dla_up.', 'ida_up.'))}
-    orc = co.DLA34Oracle(out, heads)
-    orc.calibrate = True
-    img, pre, hm = synthetic_inputs(1, 128, 160, seed=seed + 1)
-    has_pre = 'base.pre_img_layer.0.weight' in out
-    has_hm = 'base.pre_hm_layer.0.weight' in out
-    orc.feats(img, pre if has_pre else None, hm if has_hm else None)
+  if calibrated:
+    import numpy as np
+    path = calib_path(seed)
+    if not os.path.exists(path):
+      raise RuntimeError('%s missing: run `python oracle/calibrate.py %d`' % (path, seed))
+    stats = np.load(path)
     for k in out:
-      if k.endswith('running_mean') or k.endswith('running_var'):
-        out[k] = orc.sd[k].to(out[k].dtype).clone()
+      if (k.endswith('running_mean') or k.endswith('running_var')) and k in stats.files:
+        out[k] = torch.from_numpy(stats[k]).to(out[k].dtype)
   _cache[ck] = {k: v.clone() for k, v in out.items()}
   return out
 

@@ -15,7 +15,8 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 import ref_harness as rh          # noqa
-import weights as wt              # noqa
+sys.path.insert(0, os.path.join(HERE, '..'))
+from centertrack_b200 import synthetic as wt   # noqa
 
 OUT = os.path.join(HERE, '..', 'tests', 'golden')
 SMALL_HW = (64, 96)

@@ -10,7 +10,7 @@ for p in (ROOT, os.path.join(ROOT, 'oracle')):
   if p not in sys.path:
     sys.path.insert(0, p)
 
-import weights as wt        # noqa: E402  (oracle/weights.py)
+from centertrack_b200 import synthetic as wt   # noqa: E402
 
 TASKS = {'coco_tracking': ['tracking'], 'mot': ['tracking', '--num_classes', '1', '--input_h', '544',
                                                  '--input_w', '960'],

@@ -1,0 +1,159 @@
+"""-m gpu: the conv / DCN engines through ct_conv_forward (C ABI) vs torch fp32 on CPU.
+Tolerances: SIMT fp32 <= 2e-5 x scale (fp32 summation order); bf16 engines are compared against the
+fp32 result on bf16-ROUNDED operands, <= 6e-3 x scale = one bf16 output rounding (2^-8) + slack."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import ct_oracle as co
+from centertrack_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+ENGINES = [('simt_f32', L.CT_ENGINE_SIMT, L.CT_F32, 2e-5), ('simt_bf16', L.CT_ENGINE_SIMT, L.CT_BF16, 6e-3),
+           ('tcgen05', L.CT_ENGINE_TCGEN05, L.CT_BF16, 6e-3)]
+
+
+def _close(got, ref, tol):
+  err = (got.float().cpu() - ref).abs().max().item()
+  assert err <= tol * max(1.0, ref.abs().max().item()), 'max err %.3e (ref max %.3e)' % (err, ref.abs().max().item())
+
+
+def _case_list():
+  from gpu_helpers import conv_cases
+  return conv_cases()
+
+
+@pytest.mark.parametrize('eng', ENGINES, ids=[e[0] for e in ENGINES])
+@pytest.mark.parametrize('case', range(7))
+def test_conv_bn_residual_relu(eng, case):
+  from gpu_helpers import run_conv
+  _, engine, dtype, tol = eng
+  name, B, Cin, Cout, H, W, k, s, res, ld_pad, ch_off = _case_list()[case]
+  g = torch.Generator().manual_seed(case)
+  x = torch.randn(B, Cin, H, W, generator=g)
+  w = torch.randn(Cout, Cin, k, k, generator=g) * (2.0 / (Cin * k * k)) ** 0.5
+  b = torch.randn(Cout, generator=g) * 0.1
+  OH, OW = (H + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
+  r = torch.randn(B, Cout, OH, OW, generator=g) if res else None
+  bf = dtype == L.CT_BF16
+  xq = x.bfloat16().float() if bf else x
+  rq = (r.bfloat16().float() if bf else r) if res else None
+  wq = w.bfloat16().float() if engine == L.CT_ENGINE_TCGEN05 else w
+  ref = F.conv2d(xq, wq, b, s, k // 2)
+  ref = F.relu(ref + rq if res else ref)
+  got = run_conv(engine, dtype, x.cuda(), w, b, s, True, r.cuda() if res else None, ld_pad=ld_pad, ch_off=ch_off)
+  _close(got, ref, tol)
+
+
+@pytest.mark.parametrize('eng', ENGINES, ids=[e[0] for e in ENGINES])
+@pytest.mark.parametrize('cout_act', [(2, 0), (80, 1), (1, 2), (17, 1)])
+def test_head_1x1_writes_reference_layout_with_fused_activation(eng, cout_act):
+  from gpu_helpers import run_conv
+  _, engine, dtype, tol = eng
+  Cout, act = cout_act
+  g = torch.Generator().manual_seed(Cout)
+  x = torch.randn(2, 256, 16, 24, generator=g)
+  w = torch.randn(Cout, 256, 1, 1, generator=g) * 0.05
+  b = torch.randn(Cout, generator=g)
+  xq = x.bfloat16().float() if dtype == L.CT_BF16 else x
+  wq = w.bfloat16().float() if engine == L.CT_ENGINE_TCGEN05 else w
+  ref = F.conv2d(xq, wq, b)
+  if act == 1:
+    ref = torch.sigmoid(ref)
+  if act == 2:
+    ref = 1. / (torch.sigmoid(ref) + 1e-6) - 1.
+  got = run_conv(engine, dtype, x.cuda(), w, b, 1, False, out_mode=L.CT_OUT_NCHW_F32, head_act=act)
+  _close(got, ref, tol * (10 if act == 2 else 1))
+
+
+@pytest.mark.parametrize('eng', [ENGINES[0], ENGINES[2]], ids=['simt_f32', 'tcgen05'])
+@pytest.mark.parametrize('shape', [(1, 64, 64, 24, 40), (2, 128, 64, 16, 16), (1, 256, 256, 8, 12),
+                                   (1, 512, 256, 4, 6), (1, 64, 64, 5, 7)])
+def test_dcn_v2(eng, shape):
+  """Offset/mask conv + modulated deformable conv; large offsets push samples across and beyond the
+  border (zero padding, partial bilinear weights)."""
+  from gpu_helpers import run_conv
+  _, engine, dtype, tol = eng
+  B, Cin, Cout, H, W = shape
+  g = torch.Generator().manual_seed(H * W)
+  x = torch.randn(B, Cin, H, W, generator=g)
+  w = torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (Cin * 9)) ** 0.5
+  b = torch.randn(Cout, generator=g) * 0.1
+  wo = torch.randn(27, Cin, 3, 3, generator=g) * (0.6 / (Cin * 9) ** 0.5)
+  bo = torch.randn(27, generator=g) * 1.5
+  tc = engine == L.CT_ENGINE_TCGEN05
+  xq = x.bfloat16().float() if tc else x
+  wq, woq = (w.bfloat16().float(), wo.bfloat16().float()) if tc else (w, wo)
+  om_ref = F.conv2d(xq, woq, bo, 1, 1)
+  om_ref[:, 18:] = torch.sigmoid(om_ref[:, 18:27])
+  om = run_conv(engine, dtype, x.cuda(), wo, bo, 1, relu=False, out_mode=L.CT_OUT_NHWC_F32, sig_from=18, n_tile=32)
+  _close(om[:, :27], om_ref, 2e-5 if not tc else 1e-4)
+  # feed the DEVICE offsets to both sides so the sampling positions are identical
+  om_dev = om.permute(0, 2, 3, 1).contiguous()
+  omc = om.cpu()
+  assert float(omc[:, :18].abs().max()) > 2.0          # the case really leaves the 3x3 window
+  cols = co.dcn_sample_columns(xq, omc[:, :18], omc[:, 18:27])
+  if tc:
+    cols = cols.bfloat16().float()
+  ref = torch.einsum('ok,bkp->bop', wq.reshape(Cout, Cin * 9), cols.reshape(B, Cin * 9, H * W)).view(B, Cout, H, W)
+  ref = F.relu(ref + b.view(1, -1, 1, 1))
+  got = run_conv(engine, dtype, x.cuda(), w, b, 1, relu=True, a_mode=L.CT_A_DCN, om=om_dev)
+  _close(got, ref, 5e-5 if not tc else 8e-3)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_maxpool_and_upsample_add(dtype):
+  lib = L.lib()
+  import ctypes as C
+  ct = L.CT_F32 if dtype == torch.float32 else L.CT_BF16
+  g = torch.Generator().manual_seed(3)
+  x = torch.randn(2, 32, 12, 20, generator=g).to(dtype)
+  xn = x.permute(0, 2, 3, 1).contiguous().cuda()
+  out = torch.zeros(2, 6, 10, 48, dtype=dtype, device='cuda')          # write into a slice of a wider buffer
+  L.check(lib.ct_maxpool2(L.ptr(xn), C.c_void_p(out.data_ptr() + 8 * out.element_size()), ct, 2, 12, 20, 32, 32, 48,
+                          L.stream_ptr()))
+  ref = F.max_pool2d(x.float(), 2, 2)
+  assert torch.equal(out[..., 8:40].permute(0, 3, 1, 2).float().cpu(), ref)
+  assert float(out[..., :8].abs().max()) == 0 and float(out[..., 40:].abs().max()) == 0
+  for f in (2, 4):
+    w = torch.rand(32, 1, 2 * f, 2 * f, generator=g)
+    skip = torch.randn(2, 32, 12 * f, 20 * f, generator=g).to(dtype)
+    o = torch.empty(2, 12 * f, 20 * f, 32, dtype=dtype, device='cuda')
+    wd = w.reshape(32, 2 * f, 2 * f).contiguous().cuda()
+    sk = skip.permute(0, 2, 3, 1).contiguous().cuda()
+    L.check(lib.ct_upsample_add(L.ptr(xn), L.ptr(sk), L.ptr(wd), L.ptr(o), ct, 2, 12, 20, 32, f, 32, 32, 32,
+                                L.stream_ptr()))
+    ref = F.conv_transpose2d(x.float(), w, None, stride=f, padding=f // 2, groups=32) + skip.float()
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert (o.permute(0, 3, 1, 2).float().cpu() - ref).abs().max() < tol
+
+
+def test_stem_three_inputs_relu_before_sum():
+  lib = L.lib()
+  g = torch.Generator().manual_seed(9)
+  B, H, W = 2, 40, 56
+  img, pre, hm = torch.randn(B, 3, H, W, generator=g), torch.randn(B, 3, H, W, generator=g), torch.rand(B, 1, H, W, generator=g)
+  ws = [torch.randn(16, c, 7, 7, generator=g) * 0.1 for c in (3, 3, 1)]
+  sh = torch.randn(3, 16, generator=g) * 0.2
+  wst = torch.zeros(49, 7, 16)
+  for w, c0 in zip(ws, (0, 3, 6)):
+    wst[:, c0:c0 + w.shape[1]] = w.permute(2, 3, 1, 0).reshape(49, w.shape[1], 16)
+  ref_all = sum(F.relu(F.conv2d(t, w, s, 1, 3)) for t, w, s in zip((img, pre, hm), ws, sh))
+  ref_img = F.relu(F.conv2d(img, ws[0], sh[0], 1, 3))
+  out = torch.empty(B, H, W, 16, device='cuda')
+  wd, sd_, di, dp, dh = wst.cuda(), sh.cuda(), img.cuda(), pre.cuda(), hm.cuda()     # keep alive
+  args = (L.ptr(wd), L.ptr(sd_), L.ptr(out), L.CT_F32, B, H, W, 16, L.stream_ptr())
+  L.check(lib.ct_stem_forward(L.ptr(di), L.ptr(dp), L.ptr(dh), *args))
+  assert (out.permute(0, 3, 1, 2).cpu() - ref_all).abs().max() < 2e-5
+  L.check(lib.ct_stem_forward(L.ptr(di), L.ptr(None), L.ptr(None), *args))          # first frame of a plain detector
+  assert (out.permute(0, 3, 1, 2).cpu() - ref_img).abs().max() < 2e-5
+
+
+def test_conv_argument_validation():
+  import ctypes as C
+  lib = L.lib()
+  d = L.ConvDesc()
+  assert lib.ct_conv_forward(C.byref(d), None) == -1
+  assert b'null pointer' in lib.ct_last_error()

@@ -1,0 +1,210 @@
+"""-m gpu: whole hot path on the B200 vs the reference goldens (tests/golden, produced by the
+unmodified reference) and vs the oracle.
+
+Tolerances
+  fp32 engine : |err| <= 1e-3 x max(1, |ref|max) per tensor  (north_star's fp32 bar; DCN bilinear
+                sampling amplifies fp32 summation-order noise to ~3e-4, the same gap the reference's
+                CPU path shows against the oracle)
+  bf16 engine : |err| <= 5e-2 x max(1, |ref|max) and mean |err| <= 1e-2 x scale after ~50 bf16 layers;
+                each layer individually is within one bf16 rounding (tests/test_gpu_conv.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import ct_oracle as co
+from centertrack_b200 import synthetic as wt
+from helpers import make_model
+
+pytestmark = pytest.mark.gpu
+TOL = {'fp32': (1e-3, 2e-4), 'bf16': (5e-2, 1e-2)}
+
+
+def _check(got, ref, precision, name):
+  tol_max, tol_mean = TOL[precision]
+  got = got.detach().float().cpu().numpy()
+  scale = max(1.0, float(np.abs(ref).max()))
+  err = np.abs(got - ref)
+  assert err.max() <= tol_max * scale, '%s: max err %.3e (scale %.2f)' % (name, err.max(), scale)
+  assert err.mean() <= tol_mean * scale, '%s: mean err %.3e' % (name, err.mean())
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+@pytest.mark.parametrize('cfg', ['coco_tracking', 'mot', 'nuscenes_ddd', 'coco_pose'])
+def test_network_matches_reference_golden(cfg, precision, golden_dir):
+  g = np.load(os.path.join(golden_dir, 'net_%s_64x96.npz' % cfg))
+  opt, model, sd = make_model(cfg)
+  model = model.cuda()
+  img, pre, hm = wt.synthetic_inputs(1, 64, 96)
+  eng = model.engine_for(1, 64, 96, torch.device('cuda'), precision)
+  out = eng.forward(img.cuda(), pre.cuda(), hm.cuda())
+  torch.cuda.synchronize()
+  for h in opt.heads:
+    _check(out[h], g['head.' + h], precision, h)
+  for k in [x for x in g.files if x.startswith('stage.')]:
+    name = k[len('stage.'):]
+    _check(eng.stage('feat' if name == 'ida_up.node_2' else name), g[k], precision, name)
+  # CUDA-graph replay must be bit-identical to the eager launches
+  eager = {h: out[h].clone() for h in out}
+  eng.in_img.copy_(img); eng.in_pre.copy_(pre); eng.in_hm.copy_(hm)
+  rep = eng.replay()
+  torch.cuda.synchronize()
+  assert all(torch.equal(eager[h], rep[h]) for h in eager)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_batched_frames_are_independent(precision):
+  """B frames per launch (stream sharding unit): each frame's result equals its B=1 result."""
+  opt, model, sd = make_model('coco_tracking')
+  model = model.cuda()
+  dev = torch.device('cuda')
+  img, pre, hm = wt.synthetic_inputs(3, 64, 96, seed=5)
+  e3 = model.engine_for(3, 64, 96, dev, precision)
+  o3 = {k: v.clone() for k, v in e3.forward(img.cuda(), pre.cuda(), hm.cuda()).items()}
+  e1 = model.engine_for(1, 64, 96, dev, precision)
+  for b in range(3):
+    o1 = e1.forward(img[b:b + 1].cuda().contiguous(), pre[b:b + 1].cuda().contiguous(), hm[b:b + 1].cuda().contiguous())
+    for h in o1:
+      assert torch.equal(o1[h][0], o3[h][b]), (h, b)
+
+
+def test_first_frame_and_no_pre_hm_variants():
+  """pre_hm=None (dla.py:310) and detection-only (no pre_img either) against the oracle."""
+  opt, model, sd = make_model('coco_tracking')
+  model = model.cuda()
+  img, pre, hm = wt.synthetic_inputs(1, 64, 96, seed=8)
+  orc = co.DLA34Oracle(sd, opt.heads)
+  eng = model.engine_for(1, 64, 96, torch.device('cuda'), 'fp32')
+  for p, h in ((pre, None), (None, None)):
+    ref = orc.forward(img, p, h)
+    out = eng.forward(img.cuda(), None if p is None else p.cuda(), None if h is None else h.cuda())
+    for k in ref:
+      _check(out[k], ref[k].numpy(), 'fp32', k)
+
+
+def test_module_surface_and_dcn_module():
+  """create_model(...)(x, pre_img, pre_hm)[-1] (raw, un-sigmoided dict) and the drop-in DCN module."""
+  from centertrack_b200.dcn import DCN
+  opt, model, sd = make_model('coco_tracking', extra=['--b200_precision', 'fp32'])
+  model = model.cuda().eval()
+  img, pre, hm = wt.synthetic_inputs(1, 64, 96)
+  with torch.no_grad():
+    out = model(img.cuda(), pre.cuda(), hm.cuda())
+  assert isinstance(out, list) and len(out) == 1 and set(out[0]) == set(opt.heads)
+  ref = co.DLA34Oracle(sd, opt.heads).forward(img, pre, hm)
+  for k in ref:
+    _check(out[0][k], ref[k].numpy(), 'fp32', k)
+  opt.model_output_list = True
+  lst = model(img.cuda(), pre.cuda(), hm.cuda())[0]
+  assert isinstance(lst, list) and len(lst) == len(opt.heads)
+  # DCN module: same parameter names as upstream, forward == oracle restatement
+  d = DCN(64, 128).cuda()
+  assert sorted(k for k, _ in d.named_parameters()) == ['bias', 'conv_offset_mask.bias', 'conv_offset_mask.weight', 'weight']
+  g = torch.Generator().manual_seed(2)
+  with torch.no_grad():
+    d.conv_offset_mask.weight.copy_(torch.randn(27, 64, 3, 3, generator=g) * 0.02)
+    d.conv_offset_mask.bias.copy_(torch.randn(27, generator=g))
+    d.bias.copy_(torch.randn(128, generator=g))
+  x = torch.randn(2, 64, 12, 20, generator=g)
+  ref = co.dcn_v2_forward(x, d.weight.detach().cpu(), d.bias.detach().cpu(), d.conv_offset_mask.weight.detach().cpu(),
+                          d.conv_offset_mask.bias.detach().cpu())
+  d.precision = 'fp32'
+  assert (d(x.cuda()).cpu() - ref).abs().max() < 1e-4
+  d.precision = 'bf16'
+  assert (d(x.cuda()).cpu() - ref).abs().max() < 5e-2
+  with pytest.raises(RuntimeError, match='no CPU fallback'):
+    d(x)
+
+
+def test_checkpoint_roundtrip_and_module_prefix(tmp_path):
+  from centertrack_b200.model import create_model, load_model, save_model
+  opt, model, sd = make_model('coco_tracking')
+  path = str(tmp_path / 'model.pth')
+  torch.save({'epoch': 3, 'state_dict': {'module.' + k: v for k, v in sd.items()}}, path)   # DataParallel-style keys
+  m2 = load_model(create_model(opt.arch, opt.heads, opt.head_conv, opt=opt), path, opt)
+  assert all(torch.equal(m2.state_dict()[k], sd[k]) for k in sd)
+  save_model(path, 4, m2)
+  assert set(torch.load(path)['state_dict']) == set(sd)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_e2e_512_process_matches_reference_golden(precision, golden_dir):
+  """Config 2: coco_tracking 512x512 through Detector.process (network + fused sigmoid + fused decode)
+  against the reference's outputs: sampled head values, and the decoded detections."""
+  from centertrack_b200.detector import Detector
+  g = np.load(os.path.join(golden_dir, 'e2e_coco_tracking_512.npz'))
+  opt, model, sd = make_model('coco_tracking', extra=['--b200_precision', precision])
+  opt.load_model = ''
+  det = Detector.__new__(Detector)
+  det.opt, det.model = opt, model.cuda()
+  img, pre, hm = wt.synthetic_inputs(1, 512, 512)
+  output, dets = det.process(img.cuda(), pre.cuda(), hm.cuda(), None)
+  pos = g['pos']
+  for k in ('hm', 'reg', 'wh', 'tracking'):
+    v = output[k].cpu().numpy().reshape(output[k].shape[1], -1)[:, pos]
+    _check(torch.from_numpy(v), g['sample.' + k], precision, k)
+  ref_inds = (g['det.ys'] * 128 + g['det.xs']).astype(np.int64) + g['det.clses'].astype(np.int64) * 128 * 128
+  got_inds = (dets['ys'] * 128 + dets['xs']).astype(np.int64) + dets['clses'].astype(np.int64) * 128 * 128
+  if precision == 'fp32':
+    # identical peak set and order except where two scores are within fp32 noise of each other
+    same = (ref_inds == got_inds).mean()
+    assert same >= 0.95, same
+    assert np.abs(dets['scores'] - g['det.scores']).max() < 1e-3
+    m = ref_inds == got_inds
+    assert np.abs(dets['bboxes'][m] - g['det.bboxes'][m]).max() < 2e-3
+    assert np.abs(dets['tracking'][m] - g['det.tracking'][m]).max() < 2e-3
+  else:
+    overlap = len(set(ref_inds[0].tolist()) & set(got_inds[0].tolist())) / 100.0
+    assert overlap >= 0.80, overlap
+    assert np.abs(dets['scores'] - g['det.scores']).max() < 3e-2
+
+
+def test_detector_run_three_frames_matches_oracle_pipeline():
+  """Detector.run() on a synthetic BGR video: pre_process -> process -> post_process -> tracker, fp32
+  engine, against the same pipeline assembled from the oracle (network, decode, post-process, tracker)."""
+  from centertrack_b200.detector import Detector
+  opt, model, sd = make_model('coco_tracking', extra=['--b200_precision', 'fp32', '--track_thresh', '0.02',
+                                                       '--new_thresh', '0.02', '--input_h', '128', '--input_w', '160'])
+  opt.load_model = ''
+  from centertrack_b200 import detector as D
+  saved = D.create_model
+  D.create_model = lambda *a, **k: model
+  try:
+    det = Detector(opt)
+  finally:
+    D.create_model = saved
+  rng = np.random.RandomState(0)
+  frames = [rng.randint(0, 255, (120, 160, 3)).astype(np.uint8) for _ in range(3)]
+  orc = co.DLA34Oracle(sd, opt.heads)
+  trk = co.TrackerOracle(opt.new_thresh)
+  pre_img_t = None
+  for fi, f in enumerate(frames):
+    ret = det.run(f)
+    assert set(ret) == {'results', 'tot', 'load', 'pre', 'net', 'dec', 'post', 'merge', 'track', 'display'}
+    images, meta = det.pre_process(f, 1.0)
+    if pre_img_t is None:
+      pre_img_t = images
+      trk.init_track([])
+    phm, _ = co.render_pre_hm(trk.tracks, meta['trans_input'], meta['trans_output'], meta['inp_width'],
+                              meta['inp_height'], meta['out_width'], meta['out_height'], opt.pre_thresh)
+    out = co.sigmoid_output(orc.forward(images, pre_img_t, torch.from_numpy(phm)))
+    dets = co.generic_decode({k: v for k, v in out.items()}, opt.K)
+    dets = {k: v for k, v in dets.items() if not k.startswith('_')}
+    res = co.generic_post_process(dets, [meta['c']], [meta['s']], meta['out_height'], meta['out_width'],
+                                  opt.out_thresh, [meta['calib']])[0]
+    res = [r for r in res if r['score'] > opt.out_thresh]
+    ref = trk.step(res)
+    pre_img_t = images
+    got = ret['results']
+    assert len(got) > 0
+    # match by tracking id order; allow a few near-threshold detections to differ
+    assert abs(len(got) - len(ref)) <= max(2, len(ref) // 20)
+    n = min(len(got), len(ref))
+    ids_g = [r['tracking_id'] for r in got[:n]]
+    ids_r = [r['tracking_id'] for r in ref[:n]]
+    agree = np.mean([a == b for a, b in zip(ids_g, ids_r)])
+    assert agree >= 0.9, (fi, agree)
+    for a, b in zip(got[:n], ref[:n]):
+      if a['tracking_id'] == b['tracking_id'] and abs(a['score'] - b['score']) < 1e-4:
+        assert np.abs(np.asarray(a['bbox']) - np.asarray(b['bbox'])).max() < 0.05

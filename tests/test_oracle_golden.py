@@ -11,7 +11,7 @@ import pytest
 import torch
 
 import ct_oracle as co
-import weights as wt
+from centertrack_b200 import synthetic as wt
 from helpers import DECODE_CASES, decode_inputs, make_opt, make_model
 
 

@@ -14,10 +14,11 @@ import torch.nn.functional as F
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 from centertrack_b200 import _lib as L   # noqa
 import ct_oracle as co                    # noqa
-import weights as wt                      # noqa
+from centertrack_b200 import synthetic as wt   # noqa
 
 dev = torch.device('cuda')
 
@@ -33,65 +34,7 @@ def stat(name, got, ref, tol):
 
 
 # ------------------------------------------------------------------------------------------
-def run_conv(engine, dtype, x_nchw, w, bias, stride, relu=True, residual=None, a_mode=L.CT_A_CONV, om=None,
-             out_mode=L.CT_OUT_NHWC, n_tile=0, head_act=0, sig_from=1 << 30, ld_pad=0, ch_off=0):
-  lib = L.lib()
-  B, Cin, H, W = x_nchw.shape
-  O, _, k, _ = w.shape
-  act = torch.bfloat16 if dtype == L.CT_BF16 else torch.float32
-  ld_in = Cin + ld_pad
-  xb = torch.zeros((B, H, W, ld_in), dtype=act, device=dev)
-  xb[..., ch_off:ch_off + Cin] = x_nchw.permute(0, 2, 3, 1).to(act)
-  pad = k // 2
-  OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
-  if engine == L.CT_ENGINE_TCGEN05 and n_tile == 0:
-    n_tile = min(256, (O + 15) // 16 * 16)
-  nbytes = lib.ct_packed_weight_bytes(engine, O, Cin, k, k, n_tile)
-  wp = torch.empty(nbytes, dtype=torch.uint8)
-  w32 = w.float().contiguous()
-  L.check(lib.ct_pack_weights(engine, C.c_void_p(w32.data_ptr()), O, Cin, k, k, n_tile, C.c_void_p(wp.data_ptr())))
-  wp = wp.to(dev)
-  sh = bias.float().contiguous().to(dev)
-  d = L.ConvDesc()
-  d.engine, d.dtype, d.a_mode = engine, dtype, a_mode
-  d.B, d.H, d.W, d.C_in, d.ld_in, d.C_out = B, H, W, Cin, ld_in, O
-  d.KH = d.KW = k
-  d.stride, d.pad, d.OH, d.OW = stride, pad, OH, OW
-  d.out_mode, d.relu, d.head_act, d.sig_from, d.depth_scale, d.n_tile = out_mode, int(relu), head_act, sig_from, 1.0, n_tile
-  d.x = xb.data_ptr() + ch_off * xb.element_size()
-  d.w, d.shift = wp.data_ptr(), sh.data_ptr()
-  if residual is not None:
-    rb = residual.permute(0, 2, 3, 1).contiguous().to(act).to(dev)
-    d.residual, d.ld_res = rb.data_ptr(), O
-  if om is not None:
-    d.om, d.ld_om = om.data_ptr(), om.shape[-1]
-  if out_mode == L.CT_OUT_NCHW_F32:
-    out = torch.zeros((B, O, OH, OW), dtype=torch.float32, device=dev)
-    d.out, d.ld_out = out.data_ptr(), 0
-  elif out_mode == L.CT_OUT_NHWC_F32:
-    out = torch.zeros((B, OH, OW, 32), dtype=torch.float32, device=dev)
-    d.out, d.ld_out = out.data_ptr(), 32
-  else:
-    out = torch.zeros((B, OH, OW, O), dtype=act, device=dev)
-    d.out, d.ld_out = out.data_ptr(), O
-  L.check(lib.ct_conv_forward(C.byref(d), L.stream_ptr()), 'conv')
-  torch.cuda.synchronize()
-  if out_mode == L.CT_OUT_NCHW_F32:
-    return out
-  return out.permute(0, 3, 1, 2).float()
-
-
-def conv_cases():
-  # (name, B, Cin, Cout, H, W, k, stride, residual, ld_pad, ch_off)
-  return [
-      ('3x3 s1 64->64', 2, 64, 64, 24, 40, 3, 1, True, 0, 0),
-      ('3x3 s2 32->64', 1, 32, 64, 32, 48, 3, 2, False, 0, 0),
-      ('3x3 s1 16->16 (4 taps/slice)', 1, 16, 16, 40, 56, 3, 1, False, 0, 0),
-      ('3x3 s2 16->32', 1, 16, 32, 40, 56, 3, 2, False, 0, 0),
-      ('1x1 448->128 slice of concat', 1, 448, 128, 16, 24, 1, 1, False, 64, 32),
-      ('3x3 s1 256->512 (2 n-tiles)', 1, 256, 512, 8, 12, 3, 1, True, 0, 0),
-      ('3x3 s1 64->1024 (heads.0)', 1, 64, 1024, 16, 24, 3, 1, False, 0, 0),
-  ]
+from gpu_helpers import run_conv, conv_cases   # noqa
 
 
 def sec_conv(engine, dtype, tol):
