@@ -166,7 +166,7 @@ def main():
       dist.barrier()
     torch.cuda.synchronize(dev)
 
-  gathered = torch.empty((world,) + tuple(runner.rec.shape), device=dev) if world > 1 else None
+  gathered = torch.empty((world * B,) + tuple(runner.rec.shape[1:]), device=dev) if world > 1 else None
 
   # ---------------- device-resident timing (value) ----------------
   def dev_step():

@@ -131,7 +131,7 @@ __device__ __forceinline__ void blend8(float (&acc)[8], uint4 v, float w) {
   }
 }
 
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 conv_tc_kernel(const TcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   // SWIZZLE_128B operands need 1024B-aligned stage bases: align by hand (launch adds 1 KB of slack)
@@ -249,34 +249,44 @@ conv_tc_kernel(const TcArgs a) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) sts16(dst + i * 2048u, v[i]);
       } else {
+        // 4 rows x 4 bilinear corners = 16 independent 16-byte loads in flight per thread before any
+        // blend: the gather is latency-bound, memory-level parallelism is what buys throughput here.
         const DcnEntry* tab = dcn_tab + tap * TC_BM + r0;
-#pragma unroll 2
-        for (int i = 0; i < 8; ++i) {
-          const DcnEntry e = tab[16 * i];
-          float acc[8];
+        const uint4 zero4 = make_uint4(0, 0, 0, 0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-          if (e.m != 0.f) {
-            const int y0 = e.y0, x0 = e.x0;
-            const float hy = 1.f - e.ly, hx = 1.f - e.lx;
-            const bool y0ok = y0 >= 0, y1ok = y0 + 1 <= g.H - 1;
+        for (int half = 0; half < 2; ++half) {
+          DcnEntry e[4];
+          uint4 v[4][4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int i = half * 4 + j;
+            e[j] = tab[16 * i];
+            const int y0 = e[j].y0, x0 = e[j].x0;
+            const bool live = e[j].m != 0.f;
+            const bool y0ok = live && y0 >= 0, y1ok = live && y0 + 1 <= g.H - 1;
             const bool x0ok = x0 >= 0, x1ok = x0 + 1 <= g.W - 1;
-            const __nv_bfloat16* base = a.x + ((size_t)(row_img[i] + y0 * g.W + x0)) * g.ld_in + c;
-            uint4 v00 = make_uint4(0, 0, 0, 0), v01 = v00, v10 = v00, v11 = v00;
-            if (y0ok && x0ok) v00 = ldg_nc16(base);
-            if (y0ok && x1ok) v01 = ldg_nc16(base + g.ld_in);
-            if (y1ok && x0ok) v10 = ldg_nc16(base + (size_t)g.W * g.ld_in);
-            if (y1ok && x1ok) v11 = ldg_nc16(base + (size_t)(g.W + 1) * g.ld_in);
-            blend8(acc, v00, hy * hx * e.m);
-            blend8(acc, v01, hy * e.lx * e.m);
-            blend8(acc, v10, e.ly * hx * e.m);
-            blend8(acc, v11, e.ly * e.lx * e.m);
+            const __nv_bfloat16* base = a.x + ((ptrdiff_t)(row_img[i] + y0 * g.W + x0)) * g.ld_in + c;
+            v[j][0] = (y0ok && x0ok) ? ldg_nc16(base) : zero4;
+            v[j][1] = (y0ok && x1ok) ? ldg_nc16(base + g.ld_in) : zero4;
+            v[j][2] = (y1ok && x0ok) ? ldg_nc16(base + (ptrdiff_t)g.W * g.ld_in) : zero4;
+            v[j][3] = (y1ok && x1ok) ? ldg_nc16(base + (ptrdiff_t)(g.W + 1) * g.ld_in) : zero4;
           }
-          uint4 o;
-          __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
-          sts16(dst + i * 2048u, o);
+          for (int j = 0; j < 4; ++j) {
+            const float hy = 1.f - e[j].ly, hx = 1.f - e[j].lx, m = e[j].m;
+            float acc[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+            blend8(acc, v[j][0], hy * hx * m);
+            blend8(acc, v[j][1], hy * e[j].lx * m);
+            blend8(acc, v[j][2], e[j].ly * hx * m);
+            blend8(acc, v[j][3], e[j].ly * e[j].lx * m);
+            uint4 o;
+            __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) oh[q] = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
+            sts16(dst + (half * 4 + j) * 2048u, o);
+          }
         }
       }
       fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy

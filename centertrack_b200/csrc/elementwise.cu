@@ -93,21 +93,55 @@ __global__ void maxpool2_kernel(const T* __restrict__ x, T* __restrict__ out, in
 
 // ------------------------------------------------------------------------------------------
 // depthwise ConvTranspose2d(k=2f, stride f, pad f/2, no bias) + skip  (dla.py:529-531,543-545)
+// One thread = one output pixel x 16 bytes of channels (8 bf16 / 4 fp32): every access is a full
+// 16-byte vector, consecutive threads walk consecutive channel groups then pixels (coalesced).
+// w is channel-last: fp32 [2f][2f][C].
 // ------------------------------------------------------------------------------------------
+template <typename T> struct VecIO;
+template <> struct VecIO<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct VecIO<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(h[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+
 template <typename T>
 __global__ void upsample_add_kernel(const T* __restrict__ x, const T* __restrict__ skip,
                                     const float* __restrict__ w, T* __restrict__ out, int B, int H, int W,
                                     int C, int f, int ld_in, int ld_skip, int ld_out) {
-  const int OH = H * f, OW = W * f, pad = f / 2, k = 2 * f;
-  const size_t total = (size_t)B * OH * OW * C;
+  constexpr int V = VecIO<T>::N;
+  const int OH = H * f, OW = W * f, pad = f / 2, k = 2 * f, CV = C / V;
+  const size_t total = (size_t)B * OH * OW * CV;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
-    const int c = i % C;
-    size_t p = i / C;
+    const int c = (int)(i % CV) * V;
+    size_t p = i / CV;
     const int ox = p % OW; p /= OW;
     const int oy = p % OH;
     const int b = p / OH;
-    float acc = 0.f;
+    float acc[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) acc[q] = 0.f;
     const int iy_hi = (oy + pad) / f, ix_hi = (ox + pad) / f;
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy) {
@@ -119,13 +153,26 @@ __global__ void upsample_add_kernel(const T* __restrict__ x, const T* __restrict
         const int ix = ix_hi - dx;
         const int kx = ox + pad - ix * f;
         if (ix < 0 || ix >= W || kx >= k) continue;
-        acc = fmaf(Elem<T>::ld(x + (((size_t)b * H + iy) * W + ix) * ld_in + c),
-                   __ldg(w + ((size_t)c * k + ky) * k + kx), acc);
+        float xv[V], wv[V];
+        VecIO<T>::ld(x + (((size_t)b * H + iy) * W + ix) * ld_in + c, xv);
+        const float* wp = w + ((size_t)ky * k + kx) * C + c;
+#pragma unroll
+        for (int q = 0; q < V; q += 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(wp + q));
+          wv[q] = t.x; wv[q + 1] = t.y; wv[q + 2] = t.z; wv[q + 3] = t.w;
+        }
+#pragma unroll
+        for (int q = 0; q < V; ++q) acc[q] = fmaf(xv[q], wv[q], acc[q]);
       }
     }
     const size_t op = ((size_t)b * OH + oy) * OW + ox;
-    if (skip) acc += Elem<T>::ld(skip + op * ld_skip + c);
-    Elem<T>::st(out + op * ld_out + c, acc);
+    if (skip) {
+      float sv[V];
+      VecIO<T>::ld(skip + op * ld_skip + c, sv);
+#pragma unroll
+      for (int q = 0; q < V; ++q) acc[q] += sv[q];
+    }
+    VecIO<T>::st(out + op * ld_out + c, acc);
   }
 }
 
@@ -195,7 +242,10 @@ extern "C" int ct_upsample_add(const void* x, const void* skip, const float* w, 
                                int32_t ld_skip, int32_t ld_out, void* stream) {
   CT_REQUIRE(x && w && out, "null pointer");
   CT_REQUIRE(f == 2 || f == 4 || f == 8, "unsupported upsample factor");
-  const size_t total = (size_t)B * H * f * W * f * C;
+  const int vec = dtype == CT_F32 ? 4 : 8;
+  CT_REQUIRE(C % vec == 0 && ld_in % vec == 0 && ld_out % vec == 0 && (skip == nullptr || ld_skip % vec == 0),
+             "channels / strides must be multiples of the 16-byte vector width");
+  const size_t total = (size_t)B * H * f * W * f * (C / vec);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == CT_F32)
     upsample_add_kernel<float><<<ew_blocks(total), 256, 0, st>>>(

@@ -189,7 +189,7 @@ class DLA34Engine(object):
     self._conv(p, x, w, shift, out, 3, 1, relu=True, a_mode=L.CT_A_DCN, om=om)
 
   def _up_add(self, p, x, skip, out, f):
-    w = self._dev(self.sd[p + '.weight'].to(torch.float32).reshape(x.C, 2 * f, 2 * f).contiguous())
+    w = self._dev(self.sd[p + '.weight'].to(torch.float32).reshape(x.C, 2 * f, 2 * f).permute(1, 2, 0).contiguous())
     self.ops.append(('up', (x, skip, w, out, f), p))
     self.named[p] = out
 

@@ -93,7 +93,7 @@ typedef struct {
 int64_t ct_packed_weight_bytes(int32_t engine, int32_t C_out, int32_t C_in, int32_t KH, int32_t KW,
                                int32_t n_tile);
 /* Host-side packing.  w_oihw: fp32 [C_out, C_in, KH, KW] (already BN-scale-folded).
- * SIMT engine : fp32 [KH*KW*C_in (k = tap*C_in + c)][C_out_pad16].
+ * SIMT engine : fp32 [KH*KW*C_in (k = tap*C_in + c)][C_out padded to 64].
  * tcgen05     : bf16 tiles [n_tiles][k_slices][n_tile rows x 64 k] in the 128B-swizzled
  *               shared-memory image the MMA descriptor expects (one bulk copy per tile). */
 int ct_pack_weights(int32_t engine, const float* w_oihw, int32_t C_out, int32_t C_in, int32_t KH,
@@ -112,8 +112,8 @@ int ct_stem_forward(const float* img, const float* pre_img, const float* pre_hm,
 int ct_maxpool2(const void* x, void* out, int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t C,
                 int32_t ld_in, int32_t ld_out, void* stream);
 
-/* out[b,oy,ox,c] = skip[...] + sum_{ky,kx} x[b,(oy+pad-ky)/f,(ox+pad-kx)/f,c] * w[c,ky,kx]
- * (depthwise ConvTranspose2d, kernel 2f, stride f, pad f/2; w fp32 [C][2f][2f]). */
+/* out[b,oy,ox,c] = skip[...] + sum_{ky,kx} x[b,(oy+pad-ky)/f,(ox+pad-kx)/f,c] * w[ky,kx,c]
+ * (depthwise ConvTranspose2d, kernel 2f, stride f, pad f/2; w fp32 channel-last [2f][2f][C]). */
 int ct_upsample_add(const void* x, const void* skip, const float* w, void* out, int32_t dtype,
                     int32_t B, int32_t H, int32_t W, int32_t C, int32_t f, int32_t ld_in,
                     int32_t ld_skip, int32_t ld_out, void* stream);

@@ -121,7 +121,7 @@ def test_maxpool_and_upsample_add(dtype):
     w = torch.rand(32, 1, 2 * f, 2 * f, generator=g)
     skip = torch.randn(2, 32, 12 * f, 20 * f, generator=g).to(dtype)
     o = torch.empty(2, 12 * f, 20 * f, 32, dtype=dtype, device='cuda')
-    wd = w.reshape(32, 2 * f, 2 * f).contiguous().cuda()
+    wd = w.reshape(32, 2 * f, 2 * f).permute(1, 2, 0).contiguous().cuda()     # channel-last
     sk = skip.permute(0, 2, 3, 1).contiguous().cuda()
     L.check(lib.ct_upsample_add(L.ptr(xn), L.ptr(sk), L.ptr(wd), L.ptr(o), ct, 2, 12, 20, 32, f, 32, 32, 32,
                                 L.stream_ptr()))

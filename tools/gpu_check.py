@@ -25,11 +25,13 @@ dev = torch.device('cuda')
 
 def stat(name, got, ref, tol):
   got, ref = got.float().cpu(), ref.float().cpu()
-  err = (got - ref).abs().max().item()
+  d = (got - ref).abs()
+  err = d.max().item()
   rel = err / max(ref.abs().max().item(), 1e-12)
   ok = err <= tol * max(1.0, ref.abs().max().item())
-  print('%-44s max_abs_err %.3e  rel %.3e  ref_max %.3e  %s' % (name, err, rel, ref.abs().max().item(),
-                                                              'OK' if ok else 'FAIL'))
+  print('%-40s max %.3e rel %.3e mean %.3e p99.9 %.3e ref_max %.2e ref_std %.2e %s' % (
+      name, err, rel, d.mean().item(), torch.quantile(d.flatten()[:4000000], 0.999).item(),
+      ref.abs().max().item(), ref.std().item(), 'OK' if ok else 'FAIL'))
   return ok
 
 
