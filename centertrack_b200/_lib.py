@@ -10,14 +10,14 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libctb200.so')
 CSRC = os.path.join(_HERE, 'csrc')
-SOURCES = ['api.cu', 'conv_simt.cu', 'conv_tc.cu', 'elementwise.cu', 'decode.cu']
+SOURCES = ['api.cu', 'conv_simt.cu', 'conv_tc.cu', 'conv_halo.cu', 'elementwise.cu', 'decode.cu']
 
 # ---- enums (mirror include/ctb200.h) ----
 CT_F32, CT_BF16 = 0, 1
 CT_A_CONV, CT_A_DCN = 0, 1
 CT_OUT_NHWC, CT_OUT_NHWC_F32, CT_OUT_NCHW_F32 = 0, 1, 2
 CT_HEAD_NONE, CT_HEAD_SIGMOID, CT_HEAD_DEPTH = 0, 1, 2
-CT_ENGINE_SIMT, CT_ENGINE_TCGEN05 = 0, 1
+CT_ENGINE_SIMT, CT_ENGINE_TCGEN05, CT_ENGINE_TCGEN05_HALO = 0, 1, 2
 CT_ROLE_RAW, CT_ROLE_REG, CT_ROLE_WH, CT_ROLE_LTRB, CT_ROLE_LTRB_AMODAL, CT_ROLE_HPS = range(6)
 CT_DECODE_MAX_HEADS = 12
 CT_REC_SCORE, CT_REC_CLS, CT_REC_XS, CT_REC_YS, CT_REC_BBOX, CT_REC_IND, CT_REC_HEADS = 0, 1, 2, 3, 4, 8, 9
@@ -32,7 +32,7 @@ class ConvDesc(C.Structure):
       ('OH', C.c_int32), ('OW', C.c_int32), ('ld_out', C.c_int32), ('out_mode', C.c_int32),
       ('relu', C.c_int32), ('ld_res', C.c_int32), ('head_act', C.c_int32),
       ('sig_from', C.c_int32), ('depth_scale', C.c_float), ('ld_om', C.c_int32),
-      ('n_tile', C.c_int32),
+      ('n_tile', C.c_int32), ('epilogue_sum3', C.c_int32),
       ('x', C.c_void_p), ('w', C.c_void_p), ('shift', C.c_void_p), ('residual', C.c_void_p),
       ('om', C.c_void_p), ('out', C.c_void_p),
   ]
@@ -55,7 +55,7 @@ class DecodeDesc(C.Structure):
 
 
 EXPORTS = ['ct_packed_weight_bytes', 'ct_pack_weights', 'ct_conv_forward', 'ct_stem_forward',
-           'ct_maxpool2', 'ct_upsample_add', 'ct_decode_workspace_bytes', 'ct_decode',
+           'ct_pack_stem_input', 'ct_maxpool2', 'ct_upsample_add', 'ct_decode_workspace_bytes', 'ct_decode',
            'ct_render_pre_hm', 'ct_last_error', 'ct_abi_version', 'ct_launch_count',
            'ct_reset_launch_count']
 
@@ -99,6 +99,7 @@ def lib():
   L.ct_pack_weights.argtypes = [C.c_int32, C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p]
   L.ct_conv_forward.argtypes = [C.POINTER(ConvDesc), C.c_void_p]
   L.ct_stem_forward.argtypes = [C.c_void_p] * 6 + [C.c_int32] * 5 + [C.c_void_p]
+  L.ct_pack_stem_input.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p]
   L.ct_maxpool2.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p]
   L.ct_upsample_add.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 9 + [C.c_void_p]
   L.ct_decode_workspace_bytes.restype = C.c_int64

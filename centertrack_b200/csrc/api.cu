@@ -33,6 +33,10 @@ extern "C" int64_t ct_packed_weight_bytes(int32_t engine, int32_t C_out, int32_t
   }
   if (n_tile <= 0 || n_tile % 16 != 0 || n_tile > 256) return -1;
   const int64_t n_tiles = (C_out + n_tile - 1) / n_tile;
+  if (engine == CT_ENGINE_TCGEN05_HALO) {
+    if (!(C_in == 8 || (C_in % 16 == 0 && C_in <= 64))) return -1;
+    return n_tiles * halo_blocks(C_in, KH, KW) * (int64_t)n_tile * 32;
+  }
   return n_tiles * tc_k_slices(C_in, KH, KW) * (int64_t)n_tile * 64 * 2;
 }
 
@@ -53,6 +57,26 @@ extern "C" int ct_pack_weights(int32_t engine, const float* w, int32_t C_out, in
   }
   CT_REQUIRE(n_tile > 0 && n_tile % 16 == 0 && n_tile <= 256, "bad n_tile");
   CT_REQUIRE(C_in % 8 == 0, "C_in must be a multiple of 8 for the tcgen05 engine");
+  if (engine == CT_ENGINE_TCGEN05_HALO) {
+    CT_REQUIRE(C_in == 8 || (C_in % 16 == 0 && C_in <= 64), "halo engine: C_in in {8,16,32,48,64}");
+    const int nblk = halo_blocks(C_in, KH, KW), n_tiles = (C_out + n_tile - 1) / n_tile, groups = n_tile / 8;
+    uint16_t* o = (uint16_t*)dst;
+    memset(o, 0, (size_t)n_tiles * nblk * n_tile * 32);
+    const int pairs = (KW + 1) / 2;
+    for (int oc = 0; oc < C_out; ++oc) {
+      const int nt = oc / n_tile, r = oc % n_tile, grp = r / 8, row = r % 8;
+      for (int ky = 0; ky < KH; ++ky)
+        for (int kx = 0; kx < KW; ++kx)
+          for (int c = 0; c < C_in; ++c) {
+            int blk, kc, e;
+            if (C_in == 8) { blk = ky * pairs + kx / 2; kc = kx & 1; e = c; }
+            else { blk = (ky * KW + kx) * (C_in / 16) + c / 16; kc = (c % 16) / 8; e = c % 8; }
+            const size_t off = ((((size_t)nt * nblk + blk) * 2 + kc) * groups + grp) * 64 + row * 8 + e;
+            o[off] = f32_to_bf16_rn(w[((size_t)oc * C_in + c) * taps + ky * KW + kx]);
+          }
+    }
+    return CT_OK;
+  }
   const int ks = tc_k_slices(C_in, KH, KW);
   const int n_tiles = (C_out + n_tile - 1) / n_tile;
   uint16_t* o = (uint16_t*)dst;
@@ -87,6 +111,10 @@ extern "C" int ct_conv_forward(const ct_conv_desc* d, void* stream) {
   if (d->engine == CT_ENGINE_TCGEN05) {
     CT_REQUIRE(d->dtype == CT_BF16, "tcgen05 engine needs bf16 activations");
     return conv_forward_tc(d, st);
+  }
+  if (d->engine == CT_ENGINE_TCGEN05_HALO) {
+    CT_REQUIRE(d->dtype == CT_BF16 && d->a_mode == CT_A_CONV, "halo engine: bf16 plain convolutions");
+    return conv_forward_halo(d, st);
   }
   return fail(CT_ERR_INVALID, "unknown engine%s %ld", "", (long)d->engine);
 }

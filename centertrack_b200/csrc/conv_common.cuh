@@ -65,5 +65,7 @@ __device__ __forceinline__ float head_transform(float v, int head_act, float dep
 
 int conv_forward_simt(const ct_conv_desc* d, cudaStream_t st);
 int conv_forward_tc(const ct_conv_desc* d, cudaStream_t st);
+int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st);
+int halo_blocks(int C_in, int KH, int KW);
 
 }  // namespace ctb

@@ -1,0 +1,433 @@
+// "Halo" tcgen05 convolution for stride-1 KxK layers with few input channels (C_in <= 64):
+// the im2row-free design for the thin, high-resolution layers (stems, level0, the 64-channel 128x128
+// layers, DCN offset convs, the fused head 3x3) where a per-tap gather is LSU-bound.
+//
+//   * Output tile = 8 (x) x 16 (y) pixels = 128 GEMM rows.  Its input neighbourhood (tile + halo) is
+//     fetched ONCE by TMA tensor copies (cp.async.bulk.tensor.4d, zero fill outside the image = the
+//     conv's zero padding) as C_in/8 un-swizzled "planes" [halo_y][halo_x][8 channels]: one pixel = one
+//     16-byte K-core row, 8 consecutive pixels = one 8x16B UMMA core matrix.
+//   * NO data is rearranged per tap: the A operand of tap (ky,kx) is the same shared-memory tile
+//     addressed through a UMMA descriptor whose start address is shifted by (ky*pitch + kx) pixels
+//     (K-major, SWIZZLE_NONE: LBO = plane stride (or 16 B = next pixel when C_in == 8, pairing two
+//     taps in one K=16 MMA), SBO = halo row pitch).
+//   * Weights of one output-channel tile stay resident in shared memory for the CTA's lifetime
+//     (persistent CTAs, static tile striding); accumulators are double-buffered in TMEM so the
+//     epilogue of tile i overlaps the MMAs of tile i+1; halo tiles are double/triple buffered.
+//
+// Warp roles (192 threads): warps 0-3 epilogue (TMEM lanes 32w..32w+31), warp 4 TMA producer,
+// warp 5 TMEM allocator + MMA issuer.
+#include "conv_common.cuh"
+#include <cuda.h>
+
+namespace ctb {
+
+constexpr int HT_W = 8, HT_H = 16;       // output tile (x, y)
+constexpr int H_THREADS = 192;
+
+struct HaloArgs {
+  ConvGeom g;
+  const __nv_bfloat16* w;       // packed blocks (see ct_pack_weights, engine HALO)
+  const float* shift;
+  const __nv_bfloat16* residual;
+  void* out;
+  int n_tile, n_tiles_n, nblk, planes, pw, ph, plane_bytes, box_bytes, halo_stages, tmem_cols;
+  int tiles_x, tiles_y, tiles_total;    // spatial tiles per image / total work items (incl. n tiles)
+  int pair_taps;                        // 1: C_in == 8, one MMA = taps (kx, kx+1)
+  int sum3;                             // != 0: stem epilogue sum_g relu(group g + shift) -> 16 ch; bit g = group present
+  uint32_t w_bytes;                     // bytes of one n-tile's weights
+};
+
+// ---- PTX (same wrappers as conv_tc.cu; kept local so each TU is self-contained) ----
+__device__ __forceinline__ uint32_t h_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void h_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void h_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void h_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void h_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    if (++spins > 20000000u) __trap();
+  }
+}
+__device__ __forceinline__ void h_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void h_tma_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                         uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void h_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void h_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void h_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void h_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void h_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// K-major SWIZZLE_NONE operand descriptor: [0,14) start>>4 | [16,30) LBO>>4 (next K core matrix)
+// | [32,46) SBO>>4 (next 8-row group) | [46,48) version=1 | [61,64) layout = 0
+__device__ __forceinline__ uint64_t h_sdesc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ uint32_t h_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(H_THREADS, 2)
+conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(1024) unsigned char hsm_dyn[];
+  unsigned char* sm = hsm_dyn + ((128u - (h_smem_u32(hsm_dyn) & 127u)) & 127u);
+  const ConvGeom& g = a.g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = a.halo_stages;
+  const uint32_t halo_bytes = (uint32_t)a.planes * a.plane_bytes;
+
+  // smem: [weights][halo stage 0..S-1][barriers][tmem slot]
+  const uint32_t base = h_smem_u32(sm);
+  const uint32_t sW = base;
+  const uint32_t sH = base + ((a.w_bytes + 127u) & ~127u);
+  const uint32_t off_bar = ((a.w_bytes + 127u) & ~127u) + S * halo_bytes;
+  const uint32_t bars = base + off_bar;
+  // barriers: w_full, halo_full[S], halo_empty[S], tmem_full[2], tmem_empty[2]
+  const uint32_t w_full = bars;
+  auto halo_full = [&](int s) { return bars + 8u * (1 + s); };
+  auto halo_empty = [&](int s) { return bars + 8u * (1 + S + s); };
+  auto tmem_full = [&](int s) { return bars + 8u * (1 + 2 * S + s); };
+  auto tmem_empty = [&](int s) { return bars + 8u * (3 + 2 * S + s); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + off_bar + 8 * (5 + 2 * S));
+
+  if (tid == 0) {
+    h_mbar_init(w_full, 1);
+    for (int s = 0; s < S; ++s) { h_mbar_init(halo_full(s), 1); h_mbar_init(halo_empty(s), 1); }
+    for (int s = 0; s < 2; ++s) { h_mbar_init(tmem_full(s), 1); h_mbar_init(tmem_empty(s), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(h_smem_u32((const void*)tmem_slot)), "r"((uint32_t)a.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  h_fence_before();
+  __syncthreads();
+  h_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work items: n-tile major so that a CTA keeps ONE weight tile resident:  item = nt * spatial + sp
+  // CTA c handles n-tile (c % n_tiles_n) and spatial tiles (c / n_tiles_n) + i * (gridDim.x / n_tiles_n)
+  const int nt = blockIdx.x % a.n_tiles_n;
+  const int sp0 = blockIdx.x / a.n_tiles_n;
+  const int sp_stride = gridDim.x / a.n_tiles_n;
+  const int sp_total = a.tiles_total;
+  const int n0 = nt * a.n_tile;
+  const int per_img = a.tiles_x * a.tiles_y;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      h_mbar_expect_tx(w_full, a.w_bytes);
+      h_bulk_g2s(sW, reinterpret_cast<const unsigned char*>(a.w) + (size_t)nt * a.w_bytes, a.w_bytes, w_full);
+      int it = 0;
+      for (int sp = sp0; sp < sp_total; sp += sp_stride, ++it) {
+        const int s = it % S;
+        const uint32_t ph = (uint32_t)(it / S) & 1u;
+        h_mbar_wait(halo_empty(s), ph ^ 1u);
+        const int b = sp / per_img, r = sp - b * per_img;
+        const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
+        const int x0 = tx * HT_W - g.pad, y0 = ty * HT_H - g.pad;
+        h_mbar_expect_tx(halo_full(s), (uint32_t)(a.planes * a.box_bytes));   // TMA writes the full box (zero fill incl.)
+        for (int p = 0; p < a.planes; ++p)
+          h_tma_4d(sH + s * halo_bytes + p * a.plane_bytes, &tmap, p * 8, x0, y0, b, halo_full(s));
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      const uint32_t idesc = h_idesc(a.n_tile);
+      const uint32_t b_lbo = (uint32_t)a.n_tile * 16u, b_sbo = 128u, b_blk = (uint32_t)a.n_tile * 32u;
+      const uint32_t a_sbo = (uint32_t)a.pw * 16u;
+      const uint32_t a_lbo = a.pair_taps ? 16u : (uint32_t)a.plane_bytes;
+      h_mbar_wait(w_full, 0);
+      int it = 0;
+      for (int sp = sp0; sp < sp_total; sp += sp_stride, ++it) {
+        const int s = it % S;
+        const uint32_t ph = (uint32_t)(it / S) & 1u;
+        const int acc = it & 1;
+        const uint32_t pa = (uint32_t)(it >> 1) & 1u;
+        h_mbar_wait(halo_full(s), ph);
+        h_mbar_wait(tmem_empty(acc), pa ^ 1u);
+        h_fence_after();
+        const uint32_t hbase = sH + s * halo_bytes;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.n_tile);
+        int blk = 0;
+        if (a.pair_taps) {
+          const int pairs = (g.KW + 1) >> 1;
+          for (int ky = 0; ky < g.KH; ++ky)
+            for (int kp = 0; kp < pairs; ++kp, ++blk)
+              h_mma(d_tmem, h_sdesc(hbase + (uint32_t)(ky * a.pw + 2 * kp) * 16u, a_lbo, a_sbo),
+                    h_sdesc(sW + blk * b_blk, b_lbo, b_sbo), idesc, blk > 0 ? 1u : 0u);
+        } else {
+          const int qn = g.C_in >> 4;
+          for (int ky = 0; ky < g.KH; ++ky)
+            for (int kx = 0; kx < g.KW; ++kx)
+              for (int q = 0; q < qn; ++q, ++blk)
+                h_mma(d_tmem, h_sdesc(hbase + (uint32_t)(2 * q) * a.plane_bytes + (uint32_t)(ky * a.pw + kx) * 16u,
+                                      a_lbo, a_sbo),
+                      h_sdesc(sW + blk * b_blk, b_lbo, b_sbo), idesc, blk > 0 ? 1u : 0u);
+        }
+        h_commit(halo_empty(s));
+        h_commit(tmem_full(acc));
+      }
+    }
+  } else {
+    // ===================== epilogue warps 0..3 =====================
+    const int row = warp * 32 + lane;            // GEMM row = g*8 + r  ->  pixel (ty*16 + g, tx*8 + r)
+    const int gy = row >> 3, rx = row & 7;
+    const int HWo = g.OH * g.OW;
+    int it = 0;
+    for (int sp = sp0; sp < sp_total; sp += sp_stride, ++it) {
+      const int acc = it & 1;
+      const uint32_t pa = (uint32_t)(it >> 1) & 1u;
+      const int b = sp / per_img, r = sp - b * per_img;
+      const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
+      const int oy = ty * HT_H + gy, ox = tx * HT_W + rx;
+      const bool p_ok = oy < g.OH && ox < g.OW;
+      const size_t p = ((size_t)b * g.OH + oy) * g.OW + ox;
+      h_mbar_wait(tmem_full(acc), pa);
+      h_fence_after();
+      const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * a.n_tile);
+      if (a.sum3) {
+        // stem: three 16-channel groups, ReLU each (after its folded-BN shift), then sum (dla.py:307-311)
+        float s16[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s16[j] = 0.f;
+        for (int grp = 0; grp < 3; ++grp) {
+          uint32_t rr[16];
+          h_ld16(t_lane + grp * 16, rr);
+          if (!((a.sum3 >> grp) & 1)) continue;          // absent input (pre_img / pre_hm is None)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) s16[j] += fmaxf(__uint_as_float(rr[j]) + __ldg(a.shift + grp * 16 + j), 0.f);
+        }
+        if (p_ok) {
+          uint4 oa, ob;
+          __nv_bfloat162* pa2 = reinterpret_cast<__nv_bfloat162*>(&oa);
+          __nv_bfloat162* pb2 = reinterpret_cast<__nv_bfloat162*>(&ob);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            pa2[j] = __floats2bfloat162_rn(s16[2 * j], s16[2 * j + 1]);
+            pb2[j] = __floats2bfloat162_rn(s16[8 + 2 * j], s16[8 + 2 * j + 1]);
+          }
+          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + p * g.ld_out);
+          op[0] = oa; op[1] = ob;
+        }
+      } else {
+        for (int col = 0; col < a.n_tile; col += 16) {
+          uint32_t rr[16];
+          h_ld16(t_lane + (uint32_t)col, rr);
+          const int o0 = n0 + col;
+          if (!p_ok || o0 >= g.C_out) continue;
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
+          if (a.shift) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (o0 + j < g.C_out) v[j] += __ldg(a.shift + o0 + j);
+          }
+          if (g.out_mode == CT_OUT_NHWC) {
+            if (a.residual) {
+              const uint4* rp = reinterpret_cast<const uint4*>(a.residual + p * g.ld_res + o0);
+              const uint4 ra = __ldg(rp), rb = __ldg(rp + 1);
+              const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&ra);
+              const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&rb);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 fa = __bfloat1622float2(ha[j]), fb = __bfloat1622float2(hb[j]);
+                v[2 * j] += fa.x; v[2 * j + 1] += fa.y; v[8 + 2 * j] += fb.x; v[8 + 2 * j + 1] += fb.y;
+              }
+            }
+            if (g.relu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            uint4 oa, ob;
+            __nv_bfloat162* pa2 = reinterpret_cast<__nv_bfloat162*>(&oa);
+            __nv_bfloat162* pb2 = reinterpret_cast<__nv_bfloat162*>(&ob);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              pa2[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+              pb2[j] = __floats2bfloat162_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
+            }
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + p * g.ld_out + o0);
+            op[0] = oa; op[1] = ob;
+          } else if (g.out_mode == CT_OUT_NHWC_F32) {
+            float* op = reinterpret_cast<float*>(a.out) + p * g.ld_out + o0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (o0 + j < g.C_out) {
+                float t = v[j];
+                if (g.relu) t = fmaxf(t, 0.f);
+                if (o0 + j >= g.sig_from) t = sigmoidf_ref(t);
+                op[j] = t;
+              }
+            }
+          } else {
+            float* op = reinterpret_cast<float*>(a.out) + ((size_t)b * g.C_out + o0) * HWo + (size_t)oy * g.OW + ox;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (o0 + j < g.C_out) {
+                float t = v[j];
+                if (g.relu) t = fmaxf(t, 0.f);
+                op[(size_t)j * HWo] = head_transform(t, g.head_act, g.depth_scale);
+              }
+            }
+          }
+        }
+      }
+      h_fence_before();
+      h_mbar_arrive(tmem_empty(acc));      // 128 arrivals free this accumulator stage
+    }
+  }
+
+  h_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    h_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ---- host ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+int halo_blocks(int C_in, int KH, int KW) {
+  return C_in == 8 ? KH * ((KW + 1) / 2) : KH * KW * (C_in / 16);
+}
+
+int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
+  HaloArgs a;
+  a.g = make_geom(d);
+  const ConvGeom& g = a.g;
+  if (g.stride != 1 || g.pad != g.KH / 2 || g.KH != g.KW || g.OH != g.H || g.OW != g.W)
+    return fail(CT_ERR_INVALID, "conv_halo: stride-1 'same' convolutions only%s", "");
+  if (!(g.C_in == 8 || (g.C_in % 16 == 0 && g.C_in <= 64)) || g.ld_in % 8 != 0)
+    return fail(CT_ERR_INVALID, "conv_halo: C_in must be 8, 16, 32, 48 or 64 (ld_in %% 8 == 0)%s (%ld)", "", g.C_in);
+  const int n_tile = d->n_tile;
+  if (n_tile <= 0 || n_tile % 16 != 0 || n_tile > 256)
+    return fail(CT_ERR_INVALID, "conv_halo: bad n_tile%s (%ld)", "", n_tile);
+  if (((uintptr_t)d->x & 15) || ((uintptr_t)d->w & 15) || ((uintptr_t)d->out & 15))
+    return fail(CT_ERR_INVALID, "conv_halo: x/w/out must be 16-byte aligned%s", "");
+  a.sum3 = d->epilogue_sum3;
+  if (a.sum3 && !(g.C_out == 48 && n_tile == 48 && g.out_mode == CT_OUT_NHWC && d->shift))
+    return fail(CT_ERR_INVALID, "conv_halo: sum3 epilogue needs C_out == n_tile == 48, NHWC output, shift%s", "");
+  if (g.out_mode == CT_OUT_NHWC && !a.sum3 && (g.C_out % 16 != 0 || g.ld_out % 8 != 0))
+    return fail(CT_ERR_INVALID, "conv_halo: NHWC bf16 output needs C_out %% 16 == 0, ld_out %% 8 == 0%s", "");
+  if (d->residual && (g.out_mode != CT_OUT_NHWC || g.ld_res % 8 != 0 || ((uintptr_t)d->residual & 15)))
+    return fail(CT_ERR_INVALID, "conv_halo: residual only for NHWC bf16 outputs, 16B aligned%s", "");
+  a.w = (const __nv_bfloat16*)d->w;
+  a.shift = d->shift;
+  a.residual = (const __nv_bfloat16*)d->residual;
+  a.out = d->out;
+  a.n_tile = n_tile;
+  a.n_tiles_n = (g.C_out + n_tile - 1) / n_tile;
+  a.pair_taps = g.C_in == 8;
+  a.nblk = halo_blocks(g.C_in, g.KH, g.KW);
+  a.planes = g.C_in / 8;
+  a.pw = HT_W + g.KW - 1 + (a.pair_taps ? 1 : 0);
+  a.ph = HT_H + g.KH - 1;
+  a.box_bytes = a.pw * a.ph * 16;
+  a.plane_bytes = (a.box_bytes + 127) / 128 * 128;
+  a.w_bytes = (uint32_t)a.nblk * n_tile * 32u;
+  a.tiles_x = (g.OW + HT_W - 1) / HT_W;
+  a.tiles_y = (g.OH + HT_H - 1) / HT_H;
+  a.tiles_total = g.B * a.tiles_x * a.tiles_y;
+  int cols = 32;
+  while (cols < 2 * n_tile) cols <<= 1;
+  if (cols > 512) return fail(CT_ERR_INVALID, "conv_halo: n_tile too large for double-buffered TMEM%s", "");
+  a.tmem_cols = cols;
+  const size_t halo_bytes = (size_t)a.planes * a.plane_bytes;
+  int stages = 3;
+  auto smem_for = [&](int s) { return (size_t)((a.w_bytes + 127) & ~127u) + s * halo_bytes + 8 * (5 + 2 * s) + 16 + 256; };
+  while (stages > 2 && smem_for(stages) > 220 * 1024) --stages;
+  if (smem_for(stages) > 227 * 1024)
+    return fail(CT_ERR_UNSUPPORTED, "conv_halo: weights + halo do not fit in shared memory%s (%ld bytes)", "",
+                (long)smem_for(stages));
+  a.halo_stages = stages;
+  const size_t smem = smem_for(stages);
+
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(CT_ERR_CUDA, "conv_halo: cuTensorMapEncodeTiled entry point unavailable%s", "");
+  CUtensorMap tmap;
+  const cuuint64_t dims[4] = {(cuuint64_t)g.C_in, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
+  const cuuint64_t strides[3] = {(cuuint64_t)g.ld_in * 2, (cuuint64_t)g.W * g.ld_in * 2,
+                                 (cuuint64_t)g.H * g.W * g.ld_in * 2};
+  const cuuint32_t box[4] = {8, (cuuint32_t)a.pw, (cuuint32_t)a.ph, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->x), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(CT_ERR_CUDA, "conv_halo: cuTensorMapEncodeTiled failed%s (%ld)", "", (long)cr);
+
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    CT_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  // persistent grid: a multiple of n_tiles_n, at most (SMs x CTAs that fit) and no more than the work
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int per_sm = (int)((227 * 1024) / smem);
+  const int by_tmem = 512 / cols;
+  if (per_sm > by_tmem) per_sm = by_tmem;
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  long want = (long)sms * per_sm;
+  long groups = want / a.n_tiles_n;
+  if (groups < 1) groups = 1;
+  if (groups > a.tiles_total) groups = a.tiles_total;
+  const int grid = (int)(groups * a.n_tiles_n);
+  conv_halo_kernel<<<grid, H_THREADS, smem, st>>>(a, tmap);
+  return after_launch();
+}
+
+}  // namespace ctb

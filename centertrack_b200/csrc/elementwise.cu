@@ -72,6 +72,29 @@ stem_kernel(const float* __restrict__ img, const float* __restrict__ pre, const 
 }
 
 // ------------------------------------------------------------------------------------------
+// stem input packing for the tensor-core stem: fp32 NCHW x3 -> bf16 NHWC [.,8]
+__global__ void pack_stem_kernel(const float* __restrict__ img, const float* __restrict__ pre,
+                                 const float* __restrict__ hm, uint4* __restrict__ out, int B, int H, int W) {
+  const size_t plane = (size_t)H * W, total = (size_t)B * plane;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / plane, r = i - b * plane;
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      v[c] = __ldg(img + (b * 3 + c) * plane + r);
+      v[3 + c] = pre ? __ldg(pre + (b * 3 + c) * plane + r) : 0.f;
+    }
+    v[6] = hm ? __ldg(hm + b * plane + r) : 0.f;
+    v[7] = 0.f;
+    uint4 o;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+    out[i] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void maxpool2_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, int W, int C,
                                 int ld_in, int ld_out) {
@@ -215,6 +238,17 @@ extern "C" int ct_stem_forward(const float* img, const float* pre_img, const flo
   else
     stem_kernel<__nv_bfloat16><<<grid, ST * ST, 0, st>>>(img, pre_img, pre_hm, w, shift,
                                                          (__nv_bfloat16*)out, B, H, W, ld_out);
+  return after_launch();
+}
+
+static inline int ew_blocks(size_t total);
+
+extern "C" int ct_pack_stem_input(const float* img, const float* pre_img, const float* pre_hm, void* out,
+                                  int32_t B, int32_t H, int32_t W, void* stream) {
+  CT_REQUIRE(img && out, "null pointer");
+  CT_REQUIRE(B > 0 && H > 0 && W > 0, "bad shape");
+  const size_t total = (size_t)B * H * W;
+  pack_stem_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(img, pre_img, pre_hm, (uint4*)out, B, H, W);
   return after_launch();
 }
 

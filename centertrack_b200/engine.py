@@ -53,7 +53,7 @@ def _pow2_at_least(n):
 class DLA34Engine(object):
 
   def __init__(self, state_dict, heads, B, H, W, precision='bf16', device='cuda',
-               depth_scale=1.0, has_pre_img=True, has_pre_hm=True):
+               depth_scale=1.0, has_pre_img=True, has_pre_hm=True, use_halo=True):
     assert precision in ('bf16', 'fp32')
     assert H % 32 == 0 and W % 32 == 0, 'DLA-34 needs input sizes divisible by 32'
     self.lib = L.lib()
@@ -74,6 +74,7 @@ class DLA34Engine(object):
     self.named = {}        # name -> TV (for per-stage parity tests)
     self.head_descs = {}   # head -> final ConvDesc (to toggle the fused activation)
     self.n_sm = 148
+    self.use_halo = use_halo and precision == 'bf16'
     self._build()
     self.graph = None
 
@@ -112,19 +113,19 @@ class DLA34Engine(object):
     small = [c for c in cands if c >= 64]
     return small[-1] if small else cands[0]
 
-  def _pack(self, w, n_tile):
-    """w: float64 [O,I,kh,kw] -> packed device blob for self.engine."""
+  def _pack(self, w, n_tile, engine):
+    """w: float64 [O,I,kh,kw] -> packed device blob for `engine`."""
     w32 = w.to(torch.float32).contiguous()
     O, I, kh, kw = w32.shape
-    nbytes = self.lib.ct_packed_weight_bytes(self.engine, O, I, kh, kw, n_tile)
+    nbytes = self.lib.ct_packed_weight_bytes(engine, O, I, kh, kw, n_tile)
     assert nbytes > 0
     dst = torch.empty(nbytes, dtype=torch.uint8)
-    L.check(self.lib.ct_pack_weights(self.engine, C.c_void_p(w32.data_ptr()), O, I, kh, kw, n_tile,
+    L.check(self.lib.ct_pack_weights(engine, C.c_void_p(w32.data_ptr()), O, I, kh, kw, n_tile,
                                      C.c_void_p(dst.data_ptr())), 'ct_pack_weights')
     return self._dev(dst)
 
   def _conv(self, name, x, w, shift, out, k, stride=1, relu=True, residual=None, a_mode=L.CT_A_CONV,
-            om=None, out_mode=L.CT_OUT_NHWC, head_act=L.CT_HEAD_NONE, sig_from=1 << 30, c_out=None):
+            om=None, out_mode=L.CT_OUT_NHWC, head_act=L.CT_HEAD_NONE, sig_from=1 << 30, c_out=None, sum3=0):
     """Append one conv-like launch.  x: TV; out: TV (NHWC modes) or fp32 tensor (NCHW)."""
     C_in = x.C
     if w.shape[1] != C_in:      # input channels padded (never happens for DLA-34 tensors)
@@ -134,9 +135,19 @@ class DLA34Engine(object):
     OH = (x.H + 2 * pad - k) // stride + 1
     OW = (x.W + 2 * pad - k) // stride + 1
     P = self.B * OH * OW
-    n_tile = self._pick_n_tile(P, C_out) if self.engine == L.CT_ENGINE_TCGEN05 else 0
+    engine = self.engine
+    n_tile = self._pick_n_tile(P, C_out) if engine == L.CT_ENGINE_TCGEN05 else 0
+    if engine == L.CT_ENGINE_TCGEN05 and self.use_halo and a_mode == L.CT_A_CONV and stride == 1 and \
+        (C_in in (16, 32, 48, 64) or (C_in == 8 and sum3)):
+      # thin stride-1 layer: TMA halo tile + descriptor-shifted taps (csrc/conv_halo.cu)
+      nt = 48 if sum3 else min(128, (C_out + 15) // 16 * 16)
+      nblk = k * ((k + 1) // 2) if C_in == 8 else k * k * (C_in // 16)
+      halo = (C_in // 8) * (((8 + k - 1 + (1 if C_in == 8 else 0)) * (16 + k - 1) * 16 + 127) // 128 * 128)
+      if nblk * nt * 32 + 2 * halo <= 216 * 1024:
+        engine, n_tile = L.CT_ENGINE_TCGEN05_HALO, nt
     d = L.ConvDesc()
-    d.engine, d.dtype, d.a_mode = self.engine, self.ct_dtype, a_mode
+    d.engine, d.dtype, d.a_mode = engine, self.ct_dtype, a_mode
+    d.epilogue_sum3 = sum3
     d.B, d.H, d.W, d.C_in, d.ld_in, d.C_out = self.B, x.H, x.W, C_in, x.ld, C_out
     d.KH = d.KW = k
     d.stride, d.pad, d.OH, d.OW = stride, pad, OH, OW
@@ -144,7 +155,7 @@ class DLA34Engine(object):
     d.depth_scale = self.depth_scale
     d.n_tile = n_tile
     d.x = x.ptr
-    d.w = self._pack(w, n_tile).data_ptr()
+    d.w = self._pack(w, n_tile, engine).data_ptr()
     sh = self._dev(shift.to(torch.float32).contiguous())
     d.shift = sh.data_ptr()
     if residual is not None:
@@ -158,7 +169,7 @@ class DLA34Engine(object):
       assert out.shape[:3] == (self.B, OH, OW) and out.dtype == torch.float32
       d.out, d.ld_out = out.data_ptr(), out.shape[-1]
     else:
-      assert (out.H, out.W) == (OH, OW) and out.C == C_out, (name, out.H, out.W, out.C, OH, OW, C_out)
+      assert (out.H, out.W) == (OH, OW) and out.C == (16 if sum3 else C_out), (name, out.H, out.W, out.C, OH, OW, C_out)
       d.out, d.ld_out = out.ptr, out.ld
       self.named[name] = out
     self.ops.append(('conv', d, name))
@@ -231,7 +242,17 @@ class DLA34Engine(object):
     self.stem_w = self._dev(wst.to(f32).contiguous())
     self.stem_shift = self._dev(shst.to(f32).contiguous())
     x0 = TV(self._buf(H, W, 16), 0, 16)
-    self.ops.append(('stem', x0, 'stem'))
+    if self.use_halo:
+      # tensor-core stem: pack (img, pre, hm) -> bf16 NHWC [.,8], one 7x7 conv 8 -> 48 (block-diagonal over the
+      # three stems) whose epilogue applies ReLU per stem and sums them (dla.py:307-311)
+      x8 = TV(self._buf(H, W, 8), 0, 8)
+      self.ops.append(('pack', x8, 'stem.pack'))
+      w48 = torch.zeros((48, 8, 7, 7), dtype=torch.float64)
+      for si, (c0, cn) in enumerate(((0, 3), (3, 3), (6, 1))):
+        w48[16 * si:16 * si + 16, c0:c0 + cn] = wst[:, c0:c0 + cn, :].reshape(7, 7, cn, 16).permute(3, 2, 0, 1)
+      self.stem_desc = self._conv('stem', x8, w48, shst.reshape(48), x0, 7, 1, relu=False, sum3=7)
+    else:
+      self.ops.append(('stem', x0, 'stem'))
     self.named['stem'] = x0
 
     # ---- level0 / level1 ----
@@ -371,10 +392,14 @@ class DLA34Engine(object):
   def _run_one(self, kind, pl, name, img_ptr, pre_ptr, hm_ptr, st):
     lib = self.lib
     if kind == 'conv':
+      if pl.epilogue_sum3:          # stem: which of (img, pre_img, pre_hm) exist this call (dla.py:308-311)
+        pl.epilogue_sum3 = 1 | (2 if pre_ptr.value else 0) | (4 if hm_ptr.value else 0)
       rc = lib.ct_conv_forward(C.byref(pl), st)
     elif kind == 'stem':
       rc = lib.ct_stem_forward(img_ptr, pre_ptr, hm_ptr, L.ptr(self.stem_w), L.ptr(self.stem_shift),
                                C.c_void_p(pl.ptr), self.ct_dtype, self.B, self.H, self.W, pl.ld, st)
+    elif kind == 'pack':
+      rc = lib.ct_pack_stem_input(img_ptr, pre_ptr, hm_ptr, C.c_void_p(pl.ptr), self.B, self.H, self.W, st)
     elif kind == 'pool':
       x, o = pl
       rc = lib.ct_maxpool2(C.c_void_p(x.ptr), C.c_void_p(o.ptr), self.ct_dtype, self.B, x.H, x.W, x.C,

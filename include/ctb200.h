@@ -58,7 +58,12 @@ typedef enum {           /* per-launch transform applied to the fp32 NCHW head o
   CT_HEAD_DEPTH = 2      /* dep = 1/(sigmoid(x)+1e-6)-1, times depth_scale: detector.py:305-307 */
 } ct_head_act;
 
-typedef enum { CT_ENGINE_SIMT = 0, CT_ENGINE_TCGEN05 = 1 } ct_engine;
+typedef enum {
+  CT_ENGINE_SIMT = 0,          /* fp32 FFMA implicit GEMM (reference accuracy; fp32 or bf16 activations) */
+  CT_ENGINE_TCGEN05 = 1,       /* tcgen05 implicit GEMM, A gathered per tap (any stride, DCN) */
+  CT_ENGINE_TCGEN05_HALO = 2   /* tcgen05, TMA-loaded halo tile, taps by descriptor shift: stride-1 'same'
+                                  convs with C_in in {8,16,32,48,64} */
+} ct_engine;
 
 /* One convolution-like layer.  Activations are NHWC with an explicit pixel stride (ld, in
  * elements) so that a producer can write straight into a channel slice of a concat buffer
@@ -81,6 +86,8 @@ typedef struct {
   float   depth_scale;
   int32_t ld_om;         /* CT_A_DCN: pixel stride of `om` (fp32 NHWC, >= 27) */
   int32_t n_tile;        /* tcgen05: output-channel tile (multiple of 16, <= 256); 0 = auto */
+  int32_t epilogue_sum3; /* HALO engine, C_out == 48: out16 = sum over present groups g (bit g set) of
+                            relu(acc[16g..16g+15] + shift) -- the three DLA stems (dla.py:307-311) */
   const void* x;         /* input activations */
   const void* w;         /* packed weights: see ct_pack_weights */
   const float* shift;    /* [C_out] folded BN shift / conv bias (may be NULL) */
@@ -95,7 +102,9 @@ int64_t ct_packed_weight_bytes(int32_t engine, int32_t C_out, int32_t C_in, int3
 /* Host-side packing.  w_oihw: fp32 [C_out, C_in, KH, KW] (already BN-scale-folded).
  * SIMT engine : fp32 [KH*KW*C_in (k = tap*C_in + c)][C_out padded to 64].
  * tcgen05     : bf16 tiles [n_tiles][k_slices][n_tile rows x 64 k] in the 128B-swizzled
- *               shared-memory image the MMA descriptor expects (one bulk copy per tile). */
+ *               shared-memory image the MMA descriptor expects (one bulk copy per tile).
+ * tcgen05 halo: bf16 [n_tiles][K=16 blocks][2 K-cores][n_tile/8][8 rows][8] (un-swizzled K-major core
+ *               matrices); block = (tap, 16 channels), or (ky, tap pair) when C_in == 8. */
 int ct_pack_weights(int32_t engine, const float* w_oihw, int32_t C_out, int32_t C_in, int32_t KH,
                     int32_t KW, int32_t n_tile, void* dst);
 
@@ -108,6 +117,11 @@ int ct_conv_forward(const ct_conv_desc* d, void* stream);
 int ct_stem_forward(const float* img, const float* pre_img, const float* pre_hm, const float* w,
                     const float* shift, void* out, int32_t dtype, int32_t B, int32_t H, int32_t W,
                     int32_t ld_out, void* stream);
+
+/* (img, pre_img, pre_hm) fp32 NCHW -> bf16 NHWC [B,H,W,8] = (img0..2, pre0..2, hm, 0): the input of the
+ * tensor-core stem (CT_ENGINE_TCGEN05_HALO, 7x7, C_in = 8, epilogue_sum3).  NULL inputs give zeros. */
+int ct_pack_stem_input(const float* img, const float* pre_img, const float* pre_hm, void* out, int32_t B,
+                       int32_t H, int32_t W, void* stream);
 
 int ct_maxpool2(const void* x, void* out, int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t C,
                 int32_t ld_in, int32_t ld_out, void* stream);

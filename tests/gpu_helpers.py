@@ -10,7 +10,7 @@ dev = torch.device('cuda')
 
 
 def run_conv(engine, dtype, x_nchw, w, bias, stride, relu=True, residual=None, a_mode=L.CT_A_CONV, om=None,
-             out_mode=L.CT_OUT_NHWC, n_tile=0, head_act=0, sig_from=1 << 30, ld_pad=0, ch_off=0):
+             out_mode=L.CT_OUT_NHWC, n_tile=0, head_act=0, sig_from=1 << 30, ld_pad=0, ch_off=0, sum3=0):
   lib = L.lib()
   B, Cin, H, W = x_nchw.shape
   O, _, k, _ = w.shape
@@ -20,8 +20,8 @@ def run_conv(engine, dtype, x_nchw, w, bias, stride, relu=True, residual=None, a
   xb[..., ch_off:ch_off + Cin] = x_nchw.permute(0, 2, 3, 1).to(act)
   pad = k // 2
   OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
-  if engine == L.CT_ENGINE_TCGEN05 and n_tile == 0:
-    n_tile = min(256, (O + 15) // 16 * 16)
+  if engine in (L.CT_ENGINE_TCGEN05, L.CT_ENGINE_TCGEN05_HALO) and n_tile == 0:
+    n_tile = min(256 if engine == L.CT_ENGINE_TCGEN05 else 128, (O + 15) // 16 * 16)
   nbytes = lib.ct_packed_weight_bytes(engine, O, Cin, k, k, n_tile)
   wp = torch.empty(nbytes, dtype=torch.uint8)
   w32 = w.float().contiguous()
@@ -34,6 +34,7 @@ def run_conv(engine, dtype, x_nchw, w, bias, stride, relu=True, residual=None, a
   d.KH = d.KW = k
   d.stride, d.pad, d.OH, d.OW = stride, pad, OH, OW
   d.out_mode, d.relu, d.head_act, d.sig_from, d.depth_scale, d.n_tile = out_mode, int(relu), head_act, sig_from, 1.0, n_tile
+  d.epilogue_sum3 = sum3
   d.x = xb.data_ptr() + ch_off * xb.element_size()
   d.w, d.shift = wp.data_ptr(), sh.data_ptr()
   if residual is not None:
@@ -48,8 +49,9 @@ def run_conv(engine, dtype, x_nchw, w, bias, stride, relu=True, residual=None, a
     out = torch.zeros((B, OH, OW, 32), dtype=torch.float32, device=dev)
     d.out, d.ld_out = out.data_ptr(), 32
   else:
-    out = torch.zeros((B, OH, OW, O), dtype=act, device=dev)
-    d.out, d.ld_out = out.data_ptr(), O
+    oc = 16 if sum3 else O
+    out = torch.zeros((B, OH, OW, oc), dtype=act, device=dev)
+    d.out, d.ld_out = out.data_ptr(), oc
   L.check(lib.ct_conv_forward(C.byref(d), L.stream_ptr()), 'conv')
   torch.cuda.synchronize()
   if out_mode == L.CT_OUT_NCHW_F32:

@@ -84,6 +84,72 @@ def sec_conv(engine, dtype, tol):
   return ok
 
 
+def sec_halo(tol=6e-3):
+  """CT_ENGINE_TCGEN05_HALO vs torch fp32 on bf16-rounded operands."""
+  g = torch.Generator().manual_seed(11)
+  E, D = L.CT_ENGINE_TCGEN05_HALO, L.CT_BF16
+  ok = True
+  cases = [('3x3 64->64 res', 2, 64, 64, 24, 40, 3, True, 0), ('3x3 16->16', 1, 16, 16, 40, 56, 3, False, 0),
+           ('3x3 32->64', 1, 32, 64, 20, 28, 3, False, 0), ('1x1 64->32', 1, 64, 32, 16, 24, 1, False, 0),
+           ('3x3 64->1024 nt128', 1, 64, 1024, 16, 24, 3, False, 128), ('3x3 48->16', 1, 48, 16, 33, 17, 3, False, 0),
+           ('3x3 64->64 big', 4, 64, 64, 128, 128, 3, True, 0)]
+  for (name, B, Cin, Cout, H, W, k, res, nt) in cases:
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) * (2.0 / (Cin * k * k)) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    r = torch.randn(B, Cout, H, W, generator=g) if res else None
+    ref = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b, 1, k // 2)
+    if res:
+      ref = ref + r.bfloat16().float()
+    ref = F.relu(ref)
+    try:
+      got = run_conv(E, D, x.to(dev), w, b, 1, True, r.to(dev) if res else None, n_tile=nt)
+      ok &= stat('halo ' + name, got, ref, tol)
+    except Exception:
+      traceback.print_exc()
+      ok = False
+  # DCN offset-style output
+  x = torch.randn(1, 64, 24, 40, generator=g)
+  w = torch.randn(27, 64, 3, 3, generator=g) * 0.03
+  b = torch.randn(27, generator=g)
+  ref = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b, 1, 1)
+  ref[:, 18:] = torch.sigmoid(ref[:, 18:])
+  try:
+    got = run_conv(E, D, x.to(dev), w, b, 1, relu=False, out_mode=L.CT_OUT_NHWC_F32, sig_from=18, n_tile=32)
+    ok &= stat('halo 3x3 64->27 f32 nhwc', got[:, :27], ref, 1e-4)
+  except Exception:
+    traceback.print_exc(); ok = False
+  # heads-style NCHW output
+  x = torch.randn(2, 64, 16, 24, generator=g)
+  w = torch.randn(80, 64, 1, 1, generator=g) * 0.1
+  b = torch.randn(80, generator=g)
+  ref = torch.sigmoid(F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b))
+  try:
+    got = run_conv(E, D, x.to(dev), w, b, 1, relu=False, out_mode=L.CT_OUT_NCHW_F32, head_act=1, n_tile=80)
+    ok &= stat('halo 1x1 64->80 nchw sigmoid', got, ref, 1e-4)
+  except Exception:
+    traceback.print_exc(); ok = False
+  # stem: 7x7, C_in = 8 (img3, pre3, hm1, 0), block-diagonal 48 outputs, relu per group then sum
+  for mask in (7, 1, 3):
+    img, pre, hm = torch.randn(2, 3, 40, 56, generator=g), torch.randn(2, 3, 40, 56, generator=g), torch.rand(2, 1, 40, 56, generator=g)
+    ws = [torch.randn(16, c, 7, 7, generator=g) * 0.1 for c in (3, 3, 1)]
+    sh = torch.randn(48, generator=g) * 0.2
+    w48 = torch.zeros(48, 8, 7, 7)
+    w48[0:16, 0:3], w48[16:32, 3:6], w48[32:48, 6:7] = ws[0], ws[1], ws[2]
+    x8 = torch.cat([img, pre if mask & 2 else torch.zeros_like(pre), hm if mask & 4 else torch.zeros_like(hm),
+                    torch.zeros(2, 1, 40, 56)], 1)
+    ref = 0
+    for gi, (t, wgt) in enumerate(zip((img, pre, hm), ws)):
+      if (mask >> gi) & 1:
+        ref = ref + F.relu(F.conv2d(t.bfloat16().float(), wgt.bfloat16().float(), sh[16 * gi:16 * gi + 16], 1, 3))
+    try:
+      got = run_conv(E, D, x8.to(dev), w48, sh, 1, relu=False, n_tile=48, sum3=mask)
+      ok &= stat('halo stem 7x7 8->48 sum3 mask%d' % mask, got, ref, tol)
+    except Exception:
+      traceback.print_exc(); ok = False
+  return ok
+
+
 def sec_dcn(engine, dtype, tol):
   g = torch.Generator().manual_seed(1)
   ok = True
@@ -186,11 +252,11 @@ def build_models(cfg_heads, H, W, B=1, seed=317):
   return opt, m, sd
 
 
-def sec_net(precision, tol, cfg='coco_tracking', H=64, W=96):
+def sec_net(precision, tol, cfg='coco_tracking', H=64, W=96, emulate=False):
   opt, m, sd = build_models(cfg, H, W)
   img, pre, hm = wt.synthetic_inputs(1, H, W)
   trace = {}
-  ref = co.DLA34Oracle(sd, opt.heads).forward(img, pre, hm, trace=trace)
+  ref = co.DLA34Oracle(sd, opt.heads, emulate_bf16=emulate).forward(img, pre, hm, trace=trace)
   m = m.to(dev)
   eng = m.engine_for(1, H, W, dev, precision)
   out = eng.forward(img.to(dev), pre.to(dev), hm.to(dev))
@@ -257,12 +323,16 @@ if __name__ == '__main__':
     ok = sec_conv(L.CT_ENGINE_SIMT, L.CT_F32, 2e-5) & sec_conv(L.CT_ENGINE_SIMT, L.CT_BF16, 6e-3)
   elif sec == 'conv_tc':
     ok = sec_conv(L.CT_ENGINE_TCGEN05, L.CT_BF16, 6e-3)
+  elif sec == 'conv_halo':
+    ok = sec_halo()
   elif sec == 'dcn':
     ok = sec_dcn(L.CT_ENGINE_SIMT, L.CT_F32, 5e-5) & sec_dcn(L.CT_ENGINE_TCGEN05, L.CT_BF16, 8e-3)
   elif sec == 'net_fp32':
     ok = sec_net('fp32', 1e-3)
   elif sec == 'net_bf16':
     ok = sec_net('bf16', 6e-2)
+  elif sec == 'net_bf16_emu':
+    ok = sec_net('bf16', 2e-2, emulate=True)
   elif sec == 'time':
     ok = sec_time()
   print('==== section %s %s (%.1fs)' % (sec, 'PASSED' if ok else 'FAILED', time.time() - t0))
