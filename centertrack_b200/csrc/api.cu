@@ -101,7 +101,7 @@ extern "C" int ct_conv_forward(const ct_conv_desc* d, void* stream) {
   CT_REQUIRE(d->OH == (d->H + 2 * d->pad - d->KH) / d->stride + 1, "OH inconsistent");
   CT_REQUIRE(d->OW == (d->W + 2 * d->pad - d->KW) / d->stride + 1, "OW inconsistent");
   CT_REQUIRE(d->ld_in >= d->C_in, "ld_in < C_in");
-  CT_REQUIRE(d->out_mode == CT_OUT_NCHW_F32 || d->ld_out >= d->C_out, "ld_out < C_out");
+  CT_REQUIRE(d->out_mode == CT_OUT_NCHW_F32 || d->ld_out >= (d->epilogue_sum3 ? 16 : d->C_out), "ld_out < C_out");
   if (d->a_mode == CT_A_DCN) {
     CT_REQUIRE(d->om != nullptr && d->ld_om >= 27, "DCN needs om with ld_om >= 27");
     CT_REQUIRE(d->KH == 3 && d->KW == 3 && d->stride == 1 && d->pad == 1, "DCN is 3x3 s1 p1");

@@ -103,6 +103,79 @@ def test_dcn_v2(eng, shape):
   _close(got, ref, 5e-5 if not tc else 8e-3)
 
 
+HALO_CASES = [('3x3 64->64 +res', 2, 64, 64, 24, 40, 3, True, 0), ('3x3 16->16', 1, 16, 16, 40, 56, 3, False, 0),
+              ('3x3 32->64 ragged tile', 1, 32, 64, 20, 28, 3, False, 0), ('1x1 64->32', 1, 64, 32, 16, 24, 1, False, 0),
+              ('3x3 64->1024 8 n-tiles', 1, 64, 1024, 16, 24, 3, False, 128), ('3x3 48->16 odd size', 1, 48, 16, 33, 17, 3, False, 0),
+              ('3x3 64->64 many tiles per CTA', 4, 64, 64, 128, 128, 3, True, 0)]
+
+
+@pytest.mark.parametrize('case', range(len(HALO_CASES)), ids=[c[0] for c in HALO_CASES])
+def test_halo_engine_conv(case):
+  """CT_ENGINE_TCGEN05_HALO (TMA halo tile, taps by descriptor shift, persistent CTAs) vs torch fp32 on
+  bf16-rounded operands; covers multi-tile persistence, n-tiling, image borders and ragged tiles."""
+  from gpu_helpers import run_conv
+  name, B, Cin, Cout, H, W, k, res, nt = HALO_CASES[case]
+  g = torch.Generator().manual_seed(100 + case)
+  x = torch.randn(B, Cin, H, W, generator=g)
+  w = torch.randn(Cout, Cin, k, k, generator=g) * (2.0 / (Cin * k * k)) ** 0.5
+  b = torch.randn(Cout, generator=g) * 0.1
+  r = torch.randn(B, Cout, H, W, generator=g) if res else None
+  ref = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b, 1, k // 2)
+  ref = F.relu(ref + r.bfloat16().float() if res else ref)
+  got = run_conv(L.CT_ENGINE_TCGEN05_HALO, L.CT_BF16, x.cuda(), w, b, 1, True, r.cuda() if res else None, n_tile=nt)
+  _close(got, ref, 6e-3)
+
+
+def test_halo_engine_fp32_outputs():
+  from gpu_helpers import run_conv
+  g = torch.Generator().manual_seed(21)
+  x = torch.randn(1, 64, 24, 40, generator=g)
+  w = torch.randn(27, 64, 3, 3, generator=g) * 0.03
+  b = torch.randn(27, generator=g)
+  ref = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b, 1, 1)
+  ref[:, 18:] = torch.sigmoid(ref[:, 18:])
+  got = run_conv(L.CT_ENGINE_TCGEN05_HALO, L.CT_BF16, x.cuda(), w, b, 1, relu=False, out_mode=L.CT_OUT_NHWC_F32,
+                 sig_from=18, n_tile=32)
+  _close(got[:, :27], ref, 1e-4)
+  x = torch.randn(2, 64, 16, 24, generator=g)
+  w = torch.randn(80, 64, 1, 1, generator=g) * 0.1
+  b = torch.randn(80, generator=g)
+  ref = torch.sigmoid(F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b))
+  got = run_conv(L.CT_ENGINE_TCGEN05_HALO, L.CT_BF16, x.cuda(), w, b, 1, relu=False, out_mode=L.CT_OUT_NCHW_F32,
+                 head_act=1, n_tile=80)
+  _close(got, ref, 1e-4)
+
+
+@pytest.mark.parametrize('mask', [7, 1, 3])
+def test_halo_engine_tensor_core_stem(mask):
+  """7x7, C_in = 8 = (img3, pre3, hm1, 0), two taps per K=16 MMA, block-diagonal 48 outputs; the epilogue
+  applies ReLU per stem and sums the PRESENT stems (mask bit g) -- dla.py:305-311."""
+  from gpu_helpers import run_conv
+  g = torch.Generator().manual_seed(mask)
+  img, pre, hm = torch.randn(2, 3, 40, 56, generator=g), torch.randn(2, 3, 40, 56, generator=g), torch.rand(2, 1, 40, 56, generator=g)
+  ws = [torch.randn(16, c, 7, 7, generator=g) * 0.1 for c in (3, 3, 1)]
+  sh = torch.randn(48, generator=g) * 0.2
+  w48 = torch.zeros(48, 8, 7, 7)
+  w48[0:16, 0:3], w48[16:32, 3:6], w48[32:48, 6:7] = ws[0], ws[1], ws[2]
+  x8 = torch.cat([img, pre, hm, torch.zeros(2, 1, 40, 56)], 1)
+  ref = 0
+  for gi, (t, wgt) in enumerate(zip((img, pre, hm), ws)):
+    if (mask >> gi) & 1:
+      ref = ref + F.relu(F.conv2d(t.bfloat16().float(), wgt.bfloat16().float(), sh[16 * gi:16 * gi + 16], 1, 3))
+  got = run_conv(L.CT_ENGINE_TCGEN05_HALO, L.CT_BF16, x8.cuda(), w48, sh, 1, relu=False, n_tile=48, sum3=mask)
+  _close(got, ref, 6e-3)
+
+
+def test_pack_stem_input():
+  import ctypes as C
+  g = torch.Generator().manual_seed(4)
+  img, pre, hm = torch.randn(2, 3, 9, 13, generator=g).cuda(), torch.randn(2, 3, 9, 13, generator=g).cuda(), torch.rand(2, 1, 9, 13, generator=g).cuda()
+  out = torch.empty(2, 9, 13, 8, dtype=torch.bfloat16, device='cuda')
+  L.check(L.lib().ct_pack_stem_input(L.ptr(img), L.ptr(pre), L.ptr(None), L.ptr(out), 2, 9, 13, L.stream_ptr()))
+  ref = torch.cat([img, pre, torch.zeros_like(hm), torch.zeros_like(hm)], 1).permute(0, 2, 3, 1).bfloat16()
+  assert torch.equal(out, ref)
+
+
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 def test_maxpool_and_upsample_add(dtype):
   lib = L.lib()
