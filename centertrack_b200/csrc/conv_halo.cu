@@ -18,6 +18,8 @@
 // warp 5 TMEM allocator + MMA issuer.
 #include "conv_common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace ctb {
 
@@ -33,6 +35,10 @@ struct HaloArgs {
   int n_tile, n_tiles_n, nblk, planes, pw, ph, plane_bytes, box_bytes, halo_stages, tmem_cols;
   int tiles_x, tiles_y, tiles_total;    // spatial tiles per image / total work items (incl. n tiles)
   int pair_taps;                        // 1: C_in == 8, one MMA = taps (kx, kx+1)
+  int swz;                              // 0: un-swizzled 8-channel planes; else row bytes (32/64/128): whole
+                                        //    pixel (all C_in channels) per K-major row, hardware swizzle
+  int use_base_offset;                  // descriptor base-offset field for shifted (non swizzle-aligned) starts
+  int merged_xc;                        // 1: 3-D tensor map with (x, c) merged (C_in == ld_in == 8)
   int sum3;                             // != 0: stem epilogue sum_g relu(group g + shift) -> 16 ch; bit g = group present
   uint32_t w_bytes;                     // bytes of one n-tile's weights
 };
@@ -95,6 +101,21 @@ __device__ __forceinline__ void h_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 __device__ __forceinline__ uint64_t h_sdesc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
+// K-major hardware-swizzled rows (row = one pixel, `rb` = 32/64/128 bytes of channels).  The tap shift moves the
+// start address by whole rows, i.e. off the swizzle atom alignment: bits [49,52) carry the row phase
+// ((start >> 7) & 7 for 128B, & 3 for 64B, & 1 for 32B) so the XOR pattern the TMA wrote is reproduced.
+__device__ __forceinline__ uint64_t h_sdesc_swz(uint32_t addr, uint32_t sbo, int rb, int use_base_offset) {
+  const uint64_t layout = rb == 128 ? 2ull : (rb == 64 ? 4ull : 6ull);
+  const uint32_t phase_mask = rb == 128 ? 7u : (rb == 64 ? 3u : 1u);
+  const uint64_t boff = use_base_offset ? (uint64_t)((addr >> 7) & phase_mask) : 0ull;
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) |
+         (boff << 49) | (layout << 61);
+}
+__device__ __forceinline__ void h_tma_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
 __device__ __forceinline__ uint32_t h_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
@@ -102,7 +123,7 @@ __device__ __forceinline__ uint32_t h_idesc(int n) {
 __global__ void __launch_bounds__(H_THREADS, 2)
 conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(1024) unsigned char hsm_dyn[];
-  unsigned char* sm = hsm_dyn + ((128u - (h_smem_u32(hsm_dyn) & 127u)) & 127u);
+  unsigned char* sm = hsm_dyn + ((1024u - (h_smem_u32(hsm_dyn) & 1023u)) & 1023u);
   const ConvGeom& g = a.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = a.halo_stages;
@@ -111,8 +132,8 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
   // smem: [weights][halo stage 0..S-1][barriers][tmem slot]
   const uint32_t base = h_smem_u32(sm);
   const uint32_t sW = base;
-  const uint32_t sH = base + ((a.w_bytes + 127u) & ~127u);
-  const uint32_t off_bar = ((a.w_bytes + 127u) & ~127u) + S * halo_bytes;
+  const uint32_t sH = base + ((a.w_bytes + 1023u) & ~1023u);
+  const uint32_t off_bar = ((a.w_bytes + 1023u) & ~1023u) + S * halo_bytes;
   const uint32_t bars = base + off_bar;
   // barriers: w_full, halo_full[S], halo_empty[S], tmem_full[2], tmem_empty[2]
   const uint32_t w_full = bars;
@@ -161,8 +182,12 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
         const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
         const int x0 = tx * HT_W - g.pad, y0 = ty * HT_H - g.pad;
         h_mbar_expect_tx(halo_full(s), (uint32_t)(a.planes * a.box_bytes));   // TMA writes the full box (zero fill incl.)
-        for (int p = 0; p < a.planes; ++p)
-          h_tma_4d(sH + s * halo_bytes + p * a.plane_bytes, &tmap, p * 8, x0, y0, b, halo_full(s));
+        if (a.merged_xc) {
+          h_tma_3d(sH + s * halo_bytes, &tmap, x0 * 8, y0, b, halo_full(s));
+        } else {
+          for (int p = 0; p < a.planes; ++p)      // swizzled mode: planes == 1, the box holds all channels
+            h_tma_4d(sH + s * halo_bytes + p * a.plane_bytes, &tmap, p * 8, x0, y0, b, halo_full(s));
+        }
       }
     }
   } else if (warp == 5) {
@@ -191,6 +216,15 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
             for (int kp = 0; kp < pairs; ++kp, ++blk)
               h_mma(d_tmem, h_sdesc(hbase + (uint32_t)(ky * a.pw + 2 * kp) * 16u, a_lbo, a_sbo),
                     h_sdesc(sW + blk * b_blk, b_lbo, b_sbo), idesc, blk > 0 ? 1u : 0u);
+        } else if (a.swz) {
+          const int qn = g.C_in >> 4;
+          const uint32_t rb = (uint32_t)a.swz, sbo = (uint32_t)a.pw * rb;
+          for (int ky = 0; ky < g.KH; ++ky)
+            for (int kx = 0; kx < g.KW; ++kx)
+              for (int q = 0; q < qn; ++q, ++blk)
+                h_mma(d_tmem, h_sdesc_swz(hbase + (uint32_t)(ky * a.pw + kx) * rb + (uint32_t)q * 32u, sbo, a.swz,
+                                          a.use_base_offset),
+                      h_sdesc(sW + blk * b_blk, b_lbo, b_sbo), idesc, blk > 0 ? 1u : 0u);
         } else {
           const int qn = g.C_in >> 4;
           for (int ky = 0; ky < g.KH; ++ky)
@@ -371,11 +405,20 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
   a.n_tiles_n = (g.C_out + n_tile - 1) / n_tile;
   a.pair_taps = g.C_in == 8;
   a.nblk = halo_blocks(g.C_in, g.KH, g.KW);
-  a.planes = g.C_in / 8;
+  // operand staging mode: whole-pixel swizzled rows when C_in*2 is a swizzle width (one 32/64/128-byte TMA
+  // request per halo pixel); C_in == 8 keeps the 16-byte un-swizzled rows but merges (x, c) in the tensor map
+  // when the tensor is dense (ld_in == 8) so that one request covers a whole halo row.
+  const char* env = getenv("CTB_HALO_MODE");   // debug: "planes" forces the un-swizzled plane path
+  const bool force_planes = env && strcmp(env, "planes") == 0;
+  a.swz = (!force_planes && (g.C_in == 16 || g.C_in == 32 || g.C_in == 64)) ? g.C_in * 2 : 0;
+  const char* envb = getenv("CTB_HALO_BASEOFF");
+  a.use_base_offset = envb ? atoi(envb) : 1;
+  a.merged_xc = (g.C_in == 8 && g.ld_in == 8) ? 1 : 0;
+  a.planes = a.swz ? 1 : g.C_in / 8;
   a.pw = HT_W + g.KW - 1 + (a.pair_taps ? 1 : 0);
   a.ph = HT_H + g.KH - 1;
-  a.box_bytes = a.pw * a.ph * 16;
-  a.plane_bytes = (a.box_bytes + 127) / 128 * 128;
+  a.box_bytes = a.pw * a.ph * (a.swz ? a.swz : 16);
+  a.plane_bytes = (a.box_bytes + 1023) / 1024 * 1024;
   a.w_bytes = (uint32_t)a.nblk * n_tile * 32u;
   a.tiles_x = (g.OW + HT_W - 1) / HT_W;
   a.tiles_y = (g.OH + HT_H - 1) / HT_H;
@@ -386,7 +429,7 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
   a.tmem_cols = cols;
   const size_t halo_bytes = (size_t)a.planes * a.plane_bytes;
   int stages = 3;
-  auto smem_for = [&](int s) { return (size_t)((a.w_bytes + 127) & ~127u) + s * halo_bytes + 8 * (5 + 2 * s) + 16 + 256; };
+  auto smem_for = [&](int s) { return (size_t)((a.w_bytes + 1023) & ~1023u) + s * halo_bytes + 8 * (5 + 2 * s) + 16 + 1024; };
   while (stages > 2 && smem_for(stages) > 220 * 1024) --stages;
   if (smem_for(stages) > 227 * 1024)
     return fail(CT_ERR_UNSUPPORTED, "conv_halo: weights + halo do not fit in shared memory%s (%ld bytes)", "",
@@ -397,14 +440,26 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(CT_ERR_CUDA, "conv_halo: cuTensorMapEncodeTiled entry point unavailable%s", "");
   CUtensorMap tmap;
-  const cuuint64_t dims[4] = {(cuuint64_t)g.C_in, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
-  const cuuint64_t strides[3] = {(cuuint64_t)g.ld_in * 2, (cuuint64_t)g.W * g.ld_in * 2,
-                                 (cuuint64_t)g.H * g.W * g.ld_in * 2};
-  const cuuint32_t box[4] = {8, (cuuint32_t)a.pw, (cuuint32_t)a.ph, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
-  const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->x), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult cr;
+  if (a.merged_xc) {
+    const cuuint64_t dims[3] = {(cuuint64_t)g.W * 8, (cuuint64_t)g.H, (cuuint64_t)g.B};
+    const cuuint64_t strides[2] = {(cuuint64_t)g.W * 16, (cuuint64_t)g.H * g.W * 16};
+    const cuuint32_t box[3] = {(cuuint32_t)a.pw * 8, (cuuint32_t)a.ph, 1};
+    cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->x), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    const cuuint64_t dims[4] = {(cuuint64_t)g.C_in, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
+    const cuuint64_t strides[3] = {(cuuint64_t)g.ld_in * 2, (cuuint64_t)g.W * g.ld_in * 2,
+                                   (cuuint64_t)g.H * g.W * g.ld_in * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)(a.swz ? g.C_in : 8), (cuuint32_t)a.pw, (cuuint32_t)a.ph, 1};
+    const CUtensorMapSwizzle sw = a.swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : a.swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                  : a.swz == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->x), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   if (cr != CUDA_SUCCESS) return fail(CT_ERR_CUDA, "conv_halo: cuTensorMapEncodeTiled failed%s (%ld)", "", (long)cr);
 
   static thread_local bool attr_set = false;

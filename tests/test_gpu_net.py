@@ -247,3 +247,92 @@ def test_detector_run_three_frames_matches_oracle_pipeline():
     for a, b in zip(got[:n], ref[:n]):
       if a['tracking_id'] == b['tracking_id'] and abs(a['score'] - b['score']) < 1e-4:
         assert np.abs(np.asarray(a['bbox']) - np.asarray(b['bbox'])).max() < 0.05
+
+
+@pytest.mark.parametrize('cfg,hw', [('mot', (544, 960)), ('nuscenes_ddd', (448, 800)), ('coco_pose', (512, 512))])
+def test_full_size_configs_fp32_engine_vs_oracle(cfg, hw):
+  """BASELINE configs 3-5 at their real resolutions (ragged 8x16 tiles at 136x240 / 112x200 outputs):
+  fp32 engine vs the oracle, and the fused decode of the device's own maps vs the oracle decode."""
+  from centertrack_b200.decode import generic_decode
+  opt, model, sd = make_model(cfg)
+  model = model.cuda()
+  H, W = hw
+  img, pre, hm = wt.synthetic_inputs(1, H, W, seed=11)
+  ref = co.DLA34Oracle(sd, opt.heads).forward(img, pre, hm)
+  eng = model.engine_for(1, H, W, torch.device('cuda'), 'fp32')
+  eng.set_fused_activations(True)
+  out = dict(eng.forward(img.cuda(), pre.cuda(), hm.cuda()))
+  refs = co.sigmoid_output(ref)
+  for k in refs:
+    tol = 1e-3 if k != 'dep' else 2e-2          # dep = 1/(sigmoid+1e-6)-1 stretches small logit differences
+    r = refs[k].numpy()
+    err = np.abs(out[k].cpu().numpy() - r)
+    assert err.max() <= tol * max(1.0, np.abs(r).max()), (k, err.max())
+  dets = generic_decode(out, K=100)
+  host = {k: v.cpu().numpy() for k, v in out.items()}
+  od = co.generic_decode(host, 100)
+  assert np.array_equal(dets.inds.cpu().numpy(), od['_inds'].astype(np.int32))
+  for k in ('bboxes', 'tracking', 'scores'):
+    assert np.array_equal(dets[k].cpu().numpy().reshape(od[k].shape), od[k]), k
+
+
+@pytest.mark.parametrize('cfg,hw', [('mot', (544, 960)), ('nuscenes_ddd', (448, 800))])
+def test_full_size_configs_bf16_engine_vs_emulating_oracle(cfg, hw):
+  opt, model, sd = make_model(cfg)
+  model = model.cuda()
+  H, W = hw
+  img, pre, hm = wt.synthetic_inputs(1, H, W, seed=12)
+  emu = co.DLA34Oracle(sd, opt.heads, emulate_bf16=True).forward(img, pre, hm)
+  eng = model.engine_for(1, H, W, torch.device('cuda'), 'bf16')
+  out = eng.forward(img.cuda(), pre.cuda(), hm.cuda())
+  for h in opt.heads:
+    _check_stat(out[h], emu[h].numpy(), h, EMU_TOL)
+
+
+def test_render_pre_hm_matches_draw_umich_gaussian():
+  """ct_render_pre_hm (device max-splat) vs the oracle's draw_umich_gaussian, including gaussians clipped
+  by the image border and overlapping blobs."""
+  import ctypes as C
+  from centertrack_b200 import _lib as L
+  H, W = 96, 128
+  rng = np.random.RandomState(0)
+  boxes = []
+  ref = np.zeros((2, 1, H, W), np.float32)
+  for b in range(2):
+    for _ in range(12):
+      cx, cy, r = int(rng.randint(0, W)), int(rng.randint(0, H)), int(rng.randint(0, 20))
+      boxes.append([b, cx, cy, r, 0])
+      co.draw_umich_gaussian(ref[b, 0], (cx, cy), r)
+  bt = torch.tensor(boxes, dtype=torch.float32, device='cuda')
+  out = torch.full((2, 1, H, W), 7.0, device='cuda')
+  L.check(L.lib().ct_render_pre_hm(L.ptr(bt), len(boxes), L.ptr(out), 2, H, W, L.stream_ptr()))
+  assert np.abs(out.cpu().numpy() - ref).max() < 1e-6
+  L.check(L.lib().ct_render_pre_hm(L.ptr(None), 0, L.ptr(out), 2, H, W, L.stream_ptr()))
+  assert float(out.abs().max()) == 0.0
+
+
+def test_stream_runner_host_pipeline_matches_device_path():
+  """StreamRunner.step_host (pinned H2D on a copy stream, CUDA-graph replay, D2H of the packed records,
+  one-step software pipeline) returns exactly what the eager device path computes, step after step."""
+  from centertrack_b200.decode import generic_decode
+  from centertrack_b200.runner import StreamRunner
+  opt, model, sd = make_model('coco_tracking')
+  model = model.cuda()
+  B, H, W = 2, 64, 96
+  runner = StreamRunner(model, B, H, W, K=20, precision='bf16', device='cuda')
+  runner.warm()
+  eng = model.engine_for(B, H, W, torch.device('cuda'), 'bf16')
+  frames = [wt.synthetic_inputs(B, H, W, seed=40 + t) for t in range(4)]
+  got = []
+  for t, (img, _, hm) in enumerate(frames):
+    prev = runner.step_host(img.pin_memory(), hm.pin_memory())
+    if prev is not None:
+      got.append(prev.copy())
+  got.append(runner.fetch().copy())
+  # reference: same sequence eagerly; pre_images = previous step's images (first step: the zero-initialised slot)
+  pre = torch.zeros(B, 3, H, W, device='cuda')
+  for t, (img, _, hm) in enumerate(frames):
+    out = dict(eng.forward(img.cuda(), pre, hm.cuda()))
+    rec = generic_decode(out, K=20).records.cpu().numpy()
+    assert np.array_equal(rec, got[t]), t
+    pre = img.cuda()
