@@ -102,8 +102,10 @@ __device__ __forceinline__ uint64_t h_sdesc(uint32_t addr, uint32_t lbo, uint32_
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
 // K-major hardware-swizzled rows (row = one pixel, `rb` = 32/64/128 bytes of channels).  The tap shift moves the
-// start address by whole rows, i.e. off the swizzle atom alignment: bits [49,52) carry the row phase
-// ((start >> 7) & 7 for 128B, & 3 for 64B, & 1 for 32B) so the XOR pattern the TMA wrote is reproduced.
+// start address by whole rows, i.e. off the swizzle-atom alignment.  On B200 the MMA applies the XOR swizzle as a
+// function of the absolute shared-memory address -- exactly how the TMA wrote the tile -- so the shifted start
+// needs NO base-offset correction (bits [49,52) stay 0; setting them to (start>>7)&7 gives wrong results:
+// gpurun_out/halo_probe.txt, round 1).
 __device__ __forceinline__ uint64_t h_sdesc_swz(uint32_t addr, uint32_t sbo, int rb, int use_base_offset) {
   const uint64_t layout = rb == 128 ? 2ull : (rb == 64 ? 4ull : 6ull);
   const uint32_t phase_mask = rb == 128 ? 7u : (rb == 64 ? 3u : 1u);
@@ -412,7 +414,8 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
   const bool force_planes = env && strcmp(env, "planes") == 0;
   a.swz = (!force_planes && (g.C_in == 16 || g.C_in == 32 || g.C_in == 64)) ? g.C_in * 2 : 0;
   const char* envb = getenv("CTB_HALO_BASEOFF");
-  a.use_base_offset = envb ? atoi(envb) : 1;
+  a.use_base_offset = envb ? atoi(envb) : 0;   // measured on B200: the MMA's swizzle is a pure function of the
+                                                // shared-memory address (same as the TMA's), no base offset needed
   a.merged_xc = (g.C_in == 8 && g.ld_in == 8) ? 1 : 0;
   a.planes = a.swz ? 1 : g.C_in / 8;
   a.pw = HT_W + g.KW - 1 + (a.pair_taps ? 1 : 0);

@@ -14,17 +14,19 @@
 //   then bf16 NHWC / fp32 NHWC (DCN offsets, sigmoid on the mask channels) / fp32 NCHW (heads,
 //   sigmoid / depth transform) stores.
 //
-// CTA = 160 threads: warps 0-3 producers then epilogue (warp w owns TMEM lanes 32w..32w+31),
-// warp 4 = TMEM allocator + MMA issuer.  Several CTAs are co-resident per SM (<= 512 TMEM columns)
-// so one CTA's epilogue overlaps another's main loop.
+// CTA = 288 threads: warps 0-7 producers then epilogue (warp w reads TMEM lanes 32(w%4).., warps 0-3 the even
+// 16-column chunks, warps 4-7 the odd ones), warp 8 = TMEM allocator + MMA issuer.  Eight producer warps
+// (two per SM sub-partition) because the gather is latency-bound: more warps = more loads in flight.
+// Two CTAs are co-resident per SM so one CTA's epilogue overlaps another's main loop.
 #include "conv_common.cuh"
 
 namespace ctb {
 
 constexpr int TC_BM = 128;           // output pixels per CTA (UMMA M)
 constexpr int TC_BK = 64;            // K elements per pipeline stage (one 128B swizzle atom of bf16)
-constexpr int TC_THREADS = 160;
-constexpr int TC_PRODUCERS = 128;
+constexpr int TC_THREADS = 288;        // 8 producer/epilogue warps + 1 MMA warp
+constexpr int TC_PRODUCERS = 256;
+constexpr int TC_NROW = TC_BM * 8 / TC_PRODUCERS;   // A-tile rows per producer thread per K slice (4)
 constexpr int A_STAGE_BYTES = TC_BM * 128;
 
 struct TcArgs {
@@ -162,7 +164,7 @@ conv_tc_kernel(const TcArgs a) {
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32((const void*)tmem_slot)),
                  "r"((uint32_t)a.tmem_cols)
@@ -174,16 +176,16 @@ conv_tc_kernel(const TcArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // =========================== A producers ===========================
     const int q = tid & 7;                 // 16-byte chunk (8 channels) inside the 64-wide K slice
-    const int r0 = tid >> 3;               // rows r0 + 16*i
+    const int r0 = tid >> 3;               // rows r0 + 32*i, i < TC_NROW
     const uint32_t swz = (uint32_t)((q ^ (r0 & 7)) << 4);
     const int HWo = g.OH * g.OW;
-    int row_img[8], row_iy[8], row_ix[8];   // image base pixel, top-left input coords of the window
+    int row_img[TC_NROW], row_iy[TC_NROW], row_ix[TC_NROW];   // image base pixel, top-left input coords of the window
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int p = m0 + r0 + 16 * i;
+    for (int i = 0; i < TC_NROW; ++i) {
+      const int p = m0 + r0 + 32 * i;
       if (p < g.P_out) {
         const int b = p / HWo, r = p - b * HWo;
         const int oy = r / g.OW, ox = r - oy * g.OW;
@@ -195,9 +197,9 @@ conv_tc_kernel(const TcArgs a) {
       }
     }
     if (a.a_mode == CT_A_DCN) {
-      // per (tap,row) sampling parameters, computed once per CTA (row = tid)
+      // per (tap,row) sampling parameters, computed once per CTA (row = tid, threads 0..127)
       const int p = m0 + tid;
-      const bool ok = p < g.P_out;
+      const bool ok = p < g.P_out && tid < TC_BM;
       int oy = 0, ox = 0;
       if (ok) { const int r = p % HWo; oy = r / g.OW; ox = r - oy * g.OW; }
       const float* omp = a.om + (size_t)(ok ? p : 0) * g.ld_om;
@@ -213,9 +215,9 @@ conv_tc_kernel(const TcArgs a) {
             e.ly = py - y0f; e.lx = px - x0f; e.m = __ldg(omp + 18 + tap);
           }
         }
-        dcn_tab[tap * TC_BM + tid] = e;
+        if (tid < TC_BM) dcn_tab[tap * TC_BM + tid] = e;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     const int cin8 = g.C_in >> 3;
     const int ntaps = g.KH * g.KW;
@@ -235,44 +237,42 @@ conv_tc_kernel(const TcArgs a) {
       const uint32_t dst = sA + stage * A_STAGE_BYTES + (uint32_t)r0 * 128u + swz;
       if (tap >= ntaps) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) sts16(dst + i * 2048u, make_uint4(0, 0, 0, 0));
+        for (int i = 0; i < TC_NROW; ++i) sts16(dst + i * 4096u, make_uint4(0, 0, 0, 0));
       } else if (a.a_mode == CT_A_CONV) {
         const int ky = tap / g.KW, kx = tap - ky * g.KW;
-        uint4 v[8];
+        uint4 v[TC_NROW];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < TC_NROW; ++i) {
           const int iy = row_iy[i] + ky, ix = row_ix[i] + kx;
           v[i] = make_uint4(0, 0, 0, 0);
           if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
             v[i] = ldg_nc16(a.x + ((size_t)(row_img[i] + iy * g.W + ix)) * g.ld_in + c);
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) sts16(dst + i * 2048u, v[i]);
+        for (int i = 0; i < TC_NROW; ++i) sts16(dst + i * 4096u, v[i]);
       } else {
         // 4 rows x 4 bilinear corners = 16 independent 16-byte loads in flight per thread before any
         // blend: the gather is latency-bound, memory-level parallelism is what buys throughput here.
         const DcnEntry* tab = dcn_tab + tap * TC_BM + r0;
         const uint4 zero4 = make_uint4(0, 0, 0, 0);
+        {
+          DcnEntry e[TC_NROW];
+          uint4 v[TC_NROW][4];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          DcnEntry e[4];
-          uint4 v[4][4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int i = half * 4 + j;
-            e[j] = tab[16 * i];
+          for (int j = 0; j < TC_NROW; ++j) {
+            e[j] = tab[32 * j];
             const int y0 = e[j].y0, x0 = e[j].x0;
             const bool live = e[j].m != 0.f;
             const bool y0ok = live && y0 >= 0, y1ok = live && y0 + 1 <= g.H - 1;
             const bool x0ok = x0 >= 0, x1ok = x0 + 1 <= g.W - 1;
-            const __nv_bfloat16* base = a.x + ((ptrdiff_t)(row_img[i] + y0 * g.W + x0)) * g.ld_in + c;
+            const __nv_bfloat16* base = a.x + ((ptrdiff_t)(row_img[j] + y0 * g.W + x0)) * g.ld_in + c;
             v[j][0] = (y0ok && x0ok) ? ldg_nc16(base) : zero4;
             v[j][1] = (y0ok && x1ok) ? ldg_nc16(base + g.ld_in) : zero4;
             v[j][2] = (y1ok && x0ok) ? ldg_nc16(base + (ptrdiff_t)g.W * g.ld_in) : zero4;
             v[j][3] = (y1ok && x1ok) ? ldg_nc16(base + (ptrdiff_t)(g.W + 1) * g.ld_in) : zero4;
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < TC_NROW; ++j) {
             const float hy = 1.f - e[j].ly, hx = 1.f - e[j].lx, m = e[j].m;
             float acc[8];
 #pragma unroll
@@ -285,7 +285,7 @@ conv_tc_kernel(const TcArgs a) {
             __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
             for (int q = 0; q < 4; ++q) oh[q] = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
-            sts16(dst + (half * 4 + j) * 2048u, o);
+            sts16(dst + j * 4096u, o);
           }
         }
       }
@@ -296,11 +296,12 @@ conv_tc_kernel(const TcArgs a) {
     // =========================== epilogue ===========================
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    const int row = warp * 32 + lane;
+    const int wq = warp & 3, chalf = warp >> 2;      // TMEM lane quarter, column-chunk parity
+    const int row = wq * 32 + lane;
     const int p = m0 + row;
     const bool p_ok = p < g.P_out;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int col = 0; col < a.n_tile; col += 16) {
+    const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16);
+    for (int col = chalf * 16; col < a.n_tile; col += 32) {
       uint32_t r[16];
       tc_ld16(t_lane + (uint32_t)col, r);
       const int o0 = n0 + col;
@@ -382,7 +383,7 @@ conv_tc_kernel(const TcArgs a) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols)
                  : "memory");
