@@ -193,12 +193,39 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      const uint32_t idesc = h_idesc(a.n_tile);
-      const uint32_t b_lbo = (uint32_t)a.n_tile * 16u, b_sbo = 128u, b_blk = (uint32_t)a.n_tile * 32u;
+    // ===================== MMA issuer =====================
+    // One thread issues every tcgen05.mma, so its per-instruction overhead IS the MMA rate: all descriptor
+    // arithmetic is hoisted into a per-CTA table (A descriptors relative to halo stage 0, one per K=16 block;
+    // built once by the whole warp), leaving load + add + issue per MMA.
+    uint2* tabA = reinterpret_cast<uint2*>(sm + off_bar + 8 * (5 + 2 * S) + 16);
+    {
       const uint32_t a_sbo = (uint32_t)a.pw * 16u;
       const uint32_t a_lbo = a.pair_taps ? 16u : (uint32_t)a.plane_bytes;
+      const int qn = a.pair_taps ? 1 : (g.C_in >> 4);
+      const int pairs = (g.KW + 1) >> 1;
+      for (int blk = lane; blk < a.nblk; blk += 32) {
+        uint64_t dsc;
+        if (a.pair_taps) {
+          const int ky = blk / pairs, kp = blk - ky * pairs;
+          dsc = h_sdesc(sH + (uint32_t)(ky * a.pw + 2 * kp) * 16u, a_lbo, a_sbo);
+        } else {
+          const int tap = blk / qn, q = blk - tap * qn;
+          const int ky = tap / g.KW, kx = tap - ky * g.KW;
+          if (a.swz)
+            dsc = h_sdesc_swz(sH + (uint32_t)(ky * a.pw + kx) * (uint32_t)a.swz + (uint32_t)q * 32u,
+                              (uint32_t)a.pw * (uint32_t)a.swz, a.swz, a.use_base_offset);
+          else
+            dsc = h_sdesc(sH + (uint32_t)(2 * q) * a.plane_bytes + (uint32_t)(ky * a.pw + kx) * 16u, a_lbo, a_sbo);
+        }
+        tabA[blk] = make_uint2((uint32_t)dsc, (uint32_t)(dsc >> 32));
+      }
+      __syncwarp();
+    }
+    if (lane == 0) {
+      const uint32_t idesc = h_idesc(a.n_tile);
+      const uint32_t b_lbo = (uint32_t)a.n_tile * 16u, b_sbo = 128u;
+      const uint64_t b_desc0 = h_sdesc(sW, b_lbo, b_sbo);
+      const uint32_t b_step = ((uint32_t)a.n_tile * 32u) >> 4;       // descriptor start-address units (16 B)
       h_mbar_wait(w_full, 0);
       int it = 0;
       for (int sp = sp0; sp < sp_total; sp += sp_stride, ++it) {
@@ -209,32 +236,15 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
         h_mbar_wait(halo_full(s), ph);
         h_mbar_wait(tmem_empty(acc), pa ^ 1u);
         h_fence_after();
-        const uint32_t hbase = sH + s * halo_bytes;
+        const uint32_t stage_off = (uint32_t)(s * halo_bytes) >> 4;   // stays inside the 14-bit address field
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.n_tile);
-        int blk = 0;
-        if (a.pair_taps) {
-          const int pairs = (g.KW + 1) >> 1;
-          for (int ky = 0; ky < g.KH; ++ky)
-            for (int kp = 0; kp < pairs; ++kp, ++blk)
-              h_mma(d_tmem, h_sdesc(hbase + (uint32_t)(ky * a.pw + 2 * kp) * 16u, a_lbo, a_sbo),
-                    h_sdesc(sW + blk * b_blk, b_lbo, b_sbo), idesc, blk > 0 ? 1u : 0u);
-        } else if (a.swz) {
-          const int qn = g.C_in >> 4;
-          const uint32_t rb = (uint32_t)a.swz, sbo = (uint32_t)a.pw * rb;
-          for (int ky = 0; ky < g.KH; ++ky)
-            for (int kx = 0; kx < g.KW; ++kx)
-              for (int q = 0; q < qn; ++q, ++blk)
-                h_mma(d_tmem, h_sdesc_swz(hbase + (uint32_t)(ky * a.pw + kx) * rb + (uint32_t)q * 32u, sbo, a.swz,
-                                          a.use_base_offset),
-                      h_sdesc(sW + blk * b_blk, b_lbo, b_sbo), idesc, blk > 0 ? 1u : 0u);
-        } else {
-          const int qn = g.C_in >> 4;
-          for (int ky = 0; ky < g.KH; ++ky)
-            for (int kx = 0; kx < g.KW; ++kx)
-              for (int q = 0; q < qn; ++q, ++blk)
-                h_mma(d_tmem, h_sdesc(hbase + (uint32_t)(2 * q) * a.plane_bytes + (uint32_t)(ky * a.pw + kx) * 16u,
-                                      a_lbo, a_sbo),
-                      h_sdesc(sW + blk * b_blk, b_lbo, b_sbo), idesc, blk > 0 ? 1u : 0u);
+        uint64_t bd = b_desc0;
+#pragma unroll 4
+        for (int blk = 0; blk < a.nblk; ++blk) {
+          const uint2 t = tabA[blk];
+          const uint64_t ad = ((uint64_t)t.y << 32) | (uint64_t)(t.x + stage_off);
+          h_mma(d_tmem, ad, bd, idesc, blk > 0 ? 1u : 0u);
+          bd += b_step;
         }
         h_commit(halo_empty(s));
         h_commit(tmem_full(acc));
@@ -432,7 +442,7 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
   a.tmem_cols = cols;
   const size_t halo_bytes = (size_t)a.planes * a.plane_bytes;
   int stages = 3;
-  auto smem_for = [&](int s) { return (size_t)((a.w_bytes + 1023) & ~1023u) + s * halo_bytes + 8 * (5 + 2 * s) + 16 + 1024; };
+  auto smem_for = [&](int s) { return (size_t)((a.w_bytes + 1023) & ~1023u) + s * halo_bytes + 8 * (5 + 2 * s) + 16 + 8 * (size_t)a.nblk + 1024; };
   while (stages > 2 && smem_for(stages) > 220 * 1024) --stages;
   if (smem_for(stages) > 227 * 1024)
     return fail(CT_ERR_UNSUPPORTED, "conv_halo: weights + halo do not fit in shared memory%s (%ld bytes)", "",
