@@ -34,7 +34,7 @@ extern "C" int64_t ct_packed_weight_bytes(int32_t engine, int32_t C_out, int32_t
   if (n_tile <= 0 || n_tile % 16 != 0 || n_tile > 256) return -1;
   const int64_t n_tiles = (C_out + n_tile - 1) / n_tile;
   if (engine == CT_ENGINE_TCGEN05_HALO) {
-    if (!(C_in == 8 || (C_in % 16 == 0 && C_in <= 64))) return -1;
+    if (!(C_in == 8 || (C_in % 16 == 0 && C_in <= 64) || (C_in % 64 == 0 && C_in <= 256))) return -1;
     return n_tiles * halo_blocks(C_in, KH, KW) * (int64_t)n_tile * 32;
   }
   return n_tiles * tc_k_slices(C_in, KH, KW) * (int64_t)n_tile * 64 * 2;
@@ -58,7 +58,8 @@ extern "C" int ct_pack_weights(int32_t engine, const float* w, int32_t C_out, in
   CT_REQUIRE(n_tile > 0 && n_tile % 16 == 0 && n_tile <= 256, "bad n_tile");
   CT_REQUIRE(C_in % 8 == 0, "C_in must be a multiple of 8 for the tcgen05 engine");
   if (engine == CT_ENGINE_TCGEN05_HALO) {
-    CT_REQUIRE(C_in == 8 || (C_in % 16 == 0 && C_in <= 64), "halo engine: C_in in {8,16,32,48,64}");
+    CT_REQUIRE(C_in == 8 || (C_in % 16 == 0 && C_in <= 64) || (C_in % 64 == 0 && C_in <= 256),
+               "halo engine: C_in in {8,16,32,48,64,128,192,256}");
     const int nblk = halo_blocks(C_in, KH, KW), n_tiles = (C_out + n_tile - 1) / n_tile, groups = n_tile / 8;
     uint16_t* o = (uint16_t*)dst;
     memset(o, 0, (size_t)n_tiles * nblk * n_tile * 32);

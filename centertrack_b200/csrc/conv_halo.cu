@@ -1,4 +1,4 @@
-// "Halo" tcgen05 convolution for stride-1 KxK layers with few input channels (C_in <= 64):
+// "Halo" tcgen05 convolution for stride-1 KxK layers whose weights fit in shared memory (C_in 8..256):
 // the im2row-free design for the thin, high-resolution layers (stems, level0, the 64-channel 128x128
 // layers, DCN offset convs, the fused head 3x3) where a per-tap gather is LSU-bound.
 //
@@ -14,8 +14,9 @@
 //     (persistent CTAs, static tile striding); accumulators are double-buffered in TMEM so the
 //     epilogue of tile i overlaps the MMAs of tile i+1; halo tiles are double/triple buffered.
 //
-// Warp roles (192 threads): warps 0-3 epilogue (TMEM lanes 32w..32w+31), warp 4 TMA producer,
-// warp 5 TMEM allocator + MMA issuer.
+// Warp roles (320 threads): warps 0-7 epilogue (warp w reads TMEM lanes 32(w%4)..; warps 0-3 take the even
+// 16-column chunks, 4-7 the odd ones -- the epilogue is instruction-latency bound, so two warps per SM
+// sub-partition), warp 8 TMA producer, warp 9 TMEM allocator + MMA issuer.
 #include "conv_common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
@@ -24,7 +25,8 @@
 namespace ctb {
 
 constexpr int HT_W = 8, HT_H = 16;       // output tile (x, y)
-constexpr int H_THREADS = 192;
+constexpr int H_THREADS = 320;           // 8 epilogue warps + TMA warp + MMA warp
+constexpr int H_EPI_WARPS = 8;
 
 struct HaloArgs {
   ConvGeom g;
@@ -148,13 +150,20 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
   if (tid == 0) {
     h_mbar_init(w_full, 1);
     for (int s = 0; s < S; ++s) { h_mbar_init(halo_full(s), 1); h_mbar_init(halo_empty(s), 1); }
-    for (int s = 0; s < 2; ++s) { h_mbar_init(tmem_full(s), 1); h_mbar_init(tmem_empty(s), 128); }
+    for (int s = 0; s < 2; ++s) { h_mbar_init(tmem_full(s), 1); h_mbar_init(tmem_empty(s), 32 * H_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {
+  if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                  ::"r"(h_smem_u32((const void*)tmem_slot)), "r"((uint32_t)a.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // folded-BN shift / bias of this CTA's output-channel tile, staged once (read as float4 broadcasts)
+  float* s_shift = reinterpret_cast<float*>(sm + off_bar + 128);      // barriers + TMEM slot use < 128 bytes
+  {
+    const int n0s = (blockIdx.x % a.n_tiles_n) * a.n_tile;
+    for (int j = tid; j < 256; j += H_THREADS)
+      s_shift[j] = (a.shift && j < a.n_tile && n0s + j < g.C_out) ? __ldg(a.shift + n0s + j) : 0.f;
   }
   h_fence_before();
   __syncthreads();
@@ -170,7 +179,7 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
   const int n0 = nt * a.n_tile;
   const int per_img = a.tiles_x * a.tiles_y;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       // ===================== TMA producer =====================
       h_mbar_expect_tx(w_full, a.w_bytes);
@@ -187,17 +196,19 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
         if (a.merged_xc) {
           h_tma_3d(sH + s * halo_bytes, &tmap, x0 * 8, y0, b, halo_full(s));
         } else {
-          for (int p = 0; p < a.planes; ++p)      // swizzled mode: planes == 1, the box holds all channels
-            h_tma_4d(sH + s * halo_bytes + p * a.plane_bytes, &tmap, p * 8, x0, y0, b, halo_full(s));
+          // un-swizzled: one 8-channel plane per copy; swizzled: one <=64-channel chunk (whole 128-byte rows)
+          const int cstep = a.swz ? (a.swz >> 1) : 8;
+          for (int p = 0; p < a.planes; ++p)
+            h_tma_4d(sH + s * halo_bytes + p * a.plane_bytes, &tmap, p * cstep, x0, y0, b, halo_full(s));
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===================== MMA issuer =====================
     // One thread issues every tcgen05.mma, so its per-instruction overhead IS the MMA rate: all descriptor
     // arithmetic is hoisted into a per-CTA table (A descriptors relative to halo stage 0, one per K=16 block;
     // built once by the whole warp), leaving load + add + issue per MMA.
-    uint2* tabA = reinterpret_cast<uint2*>(sm + off_bar + 8 * (5 + 2 * S) + 16);
+    uint2* tabA = reinterpret_cast<uint2*>(sm + off_bar + 128 + 1024);
     {
       const uint32_t a_sbo = (uint32_t)a.pw * 16u;
       const uint32_t a_lbo = a.pair_taps ? 16u : (uint32_t)a.plane_bytes;
@@ -211,9 +222,13 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
         } else {
           const int tap = blk / qn, q = blk - tap * qn;
           const int ky = tap / g.KW, kx = tap - ky * g.KW;
-          if (a.swz)
-            dsc = h_sdesc_swz(sH + (uint32_t)(ky * a.pw + kx) * (uint32_t)a.swz + (uint32_t)q * 32u,
+          if (a.swz) {      // q-th 16-channel step: chunk (q*16)/(channels per row), 32-byte K step inside the row
+            const int per_row = a.swz >> 5;                       // K=16 steps per row (1, 2 or 4)
+            const int chunk = q / per_row, qq = q - chunk * per_row;
+            dsc = h_sdesc_swz(sH + (uint32_t)chunk * a.plane_bytes + (uint32_t)(ky * a.pw + kx) * (uint32_t)a.swz +
+                                  (uint32_t)qq * 32u,
                               (uint32_t)a.pw * (uint32_t)a.swz, a.swz, a.use_base_offset);
+          }
           else
             dsc = h_sdesc(sH + (uint32_t)(2 * q) * a.plane_bytes + (uint32_t)(ky * a.pw + kx) * 16u, a_lbo, a_sbo);
         }
@@ -251,8 +266,9 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
       }
     }
   } else {
-    // ===================== epilogue warps 0..3 =====================
-    const int row = warp * 32 + lane;            // GEMM row = g*8 + r  ->  pixel (ty*16 + g, tx*8 + r)
+    // ===================== epilogue warps 0..7 =====================
+    const int wq = warp & 3, chalf = warp >> 2;
+    const int row = wq * 32 + lane;              // GEMM row = g*8 + r  ->  pixel (ty*16 + g, tx*8 + r)
     const int gy = row >> 3, rx = row & 7;
     const int HWo = g.OH * g.OW;
     int it = 0;
@@ -266,43 +282,57 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
       const size_t p = ((size_t)b * g.OH + oy) * g.OW + ox;
       h_mbar_wait(tmem_full(acc), pa);
       h_fence_after();
-      const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * a.n_tile);
+      const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * a.n_tile);
       if (a.sum3) {
-        // stem: three 16-channel groups, ReLU each (after its folded-BN shift), then sum (dla.py:307-311)
-        float s16[16];
+        // stem: three 16-channel groups, ReLU each (after its folded-BN shift), then sum (dla.py:307-311).
+        // One warp per lane quarter does it (the sum runs across column groups of the same pixel).
+        if (chalf == 0) {
+          float s16[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) s16[j] = 0.f;
-        for (int grp = 0; grp < 3; ++grp) {
-          uint32_t rr[16];
-          h_ld16(t_lane + grp * 16, rr);
-          if (!((a.sum3 >> grp) & 1)) continue;          // absent input (pre_img / pre_hm is None)
+          for (int j = 0; j < 16; ++j) s16[j] = 0.f;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) s16[j] += fmaxf(__uint_as_float(rr[j]) + __ldg(a.shift + grp * 16 + j), 0.f);
-        }
-        if (p_ok) {
-          uint4 oa, ob;
-          __nv_bfloat162* pa2 = reinterpret_cast<__nv_bfloat162*>(&oa);
-          __nv_bfloat162* pb2 = reinterpret_cast<__nv_bfloat162*>(&ob);
+          for (int grp = 0; grp < 3; ++grp) {
+            uint32_t rr[16];
+            h_ld16(t_lane + grp * 16, rr);
+            if (!((a.sum3 >> grp) & 1)) continue;          // absent input (pre_img / pre_hm is None)
+            const float4* sh4 = reinterpret_cast<const float4*>(s_shift + grp * 16);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            pa2[j] = __floats2bfloat162_rn(s16[2 * j], s16[2 * j + 1]);
-            pb2[j] = __floats2bfloat162_rn(s16[8 + 2 * j], s16[8 + 2 * j + 1]);
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 sh = sh4[j4];
+              s16[4 * j4 + 0] += fmaxf(__uint_as_float(rr[4 * j4 + 0]) + sh.x, 0.f);
+              s16[4 * j4 + 1] += fmaxf(__uint_as_float(rr[4 * j4 + 1]) + sh.y, 0.f);
+              s16[4 * j4 + 2] += fmaxf(__uint_as_float(rr[4 * j4 + 2]) + sh.z, 0.f);
+              s16[4 * j4 + 3] += fmaxf(__uint_as_float(rr[4 * j4 + 3]) + sh.w, 0.f);
+            }
           }
-          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + p * g.ld_out);
-          op[0] = oa; op[1] = ob;
+          if (p_ok) {
+            uint4 oa, ob;
+            __nv_bfloat162* pa2 = reinterpret_cast<__nv_bfloat162*>(&oa);
+            __nv_bfloat162* pb2 = reinterpret_cast<__nv_bfloat162*>(&ob);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              pa2[j] = __floats2bfloat162_rn(s16[2 * j], s16[2 * j + 1]);
+              pb2[j] = __floats2bfloat162_rn(s16[8 + 2 * j], s16[8 + 2 * j + 1]);
+            }
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + p * g.ld_out);
+            op[0] = oa; op[1] = ob;
+          }
         }
       } else {
-        for (int col = 0; col < a.n_tile; col += 16) {
+        for (int col = chalf * 16; col < a.n_tile; col += 32) {
           uint32_t rr[16];
           h_ld16(t_lane + (uint32_t)col, rr);
           const int o0 = n0 + col;
           if (!p_ok || o0 >= g.C_out) continue;
           float v[16];
+          const float4* sh4 = reinterpret_cast<const float4*>(s_shift + col);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
-          if (a.shift) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) if (o0 + j < g.C_out) v[j] += __ldg(a.shift + o0 + j);
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 sh = sh4[j4];
+            v[4 * j4 + 0] = __uint_as_float(rr[4 * j4 + 0]) + sh.x;
+            v[4 * j4 + 1] = __uint_as_float(rr[4 * j4 + 1]) + sh.y;
+            v[4 * j4 + 2] = __uint_as_float(rr[4 * j4 + 2]) + sh.z;
+            v[4 * j4 + 3] = __uint_as_float(rr[4 * j4 + 3]) + sh.w;
           }
           if (g.out_mode == CT_OUT_NHWC) {
             if (a.residual) {
@@ -355,13 +385,13 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
         }
       }
       h_fence_before();
-      h_mbar_arrive(tmem_empty(acc));      // 128 arrivals free this accumulator stage
+      h_mbar_arrive(tmem_empty(acc));      // all epilogue threads arrive: frees this accumulator stage
     }
   }
 
   h_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     h_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols)
                  : "memory");
@@ -395,8 +425,8 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
   const ConvGeom& g = a.g;
   if (g.stride != 1 || g.pad != g.KH / 2 || g.KH != g.KW || g.OH != g.H || g.OW != g.W)
     return fail(CT_ERR_INVALID, "conv_halo: stride-1 'same' convolutions only%s", "");
-  if (!(g.C_in == 8 || (g.C_in % 16 == 0 && g.C_in <= 64)) || g.ld_in % 8 != 0)
-    return fail(CT_ERR_INVALID, "conv_halo: C_in must be 8, 16, 32, 48 or 64 (ld_in %% 8 == 0)%s (%ld)", "", g.C_in);
+  if (!(g.C_in == 8 || (g.C_in % 16 == 0 && g.C_in <= 64) || (g.C_in % 64 == 0 && g.C_in <= 256)) || g.ld_in % 8 != 0)
+    return fail(CT_ERR_INVALID, "conv_halo: C_in must be 8, 16, 32, 48, 64, 128, 192 or 256 (ld_in %% 8 == 0)%s (%ld)", "", g.C_in);
   const int n_tile = d->n_tile;
   if (n_tile <= 0 || n_tile % 16 != 0 || n_tile > 256)
     return fail(CT_ERR_INVALID, "conv_halo: bad n_tile%s (%ld)", "", n_tile);
@@ -422,12 +452,12 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
   // when the tensor is dense (ld_in == 8) so that one request covers a whole halo row.
   const char* env = getenv("CTB_HALO_MODE");   // debug: "planes" forces the un-swizzled plane path
   const bool force_planes = env && strcmp(env, "planes") == 0;
-  a.swz = (!force_planes && (g.C_in == 16 || g.C_in == 32 || g.C_in == 64)) ? g.C_in * 2 : 0;
+  a.swz = (g.C_in > 64) ? 128 : ((!force_planes && (g.C_in == 16 || g.C_in == 32 || g.C_in == 64)) ? g.C_in * 2 : 0);
   const char* envb = getenv("CTB_HALO_BASEOFF");
   a.use_base_offset = envb ? atoi(envb) : 0;   // measured on B200: the MMA's swizzle is a pure function of the
                                                 // shared-memory address (same as the TMA's), no base offset needed
   a.merged_xc = (g.C_in == 8 && g.ld_in == 8) ? 1 : 0;
-  a.planes = a.swz ? 1 : g.C_in / 8;
+  a.planes = a.swz ? (g.C_in * 2 + a.swz - 1) / a.swz : g.C_in / 8;   // swizzled: 64-channel chunks
   a.pw = HT_W + g.KW - 1 + (a.pair_taps ? 1 : 0);
   a.ph = HT_H + g.KH - 1;
   a.box_bytes = a.pw * a.ph * (a.swz ? a.swz : 16);
@@ -442,7 +472,7 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
   a.tmem_cols = cols;
   const size_t halo_bytes = (size_t)a.planes * a.plane_bytes;
   int stages = 3;
-  auto smem_for = [&](int s) { return (size_t)((a.w_bytes + 1023) & ~1023u) + s * halo_bytes + 8 * (5 + 2 * s) + 16 + 8 * (size_t)a.nblk + 1024; };
+  auto smem_for = [&](int s) { return (size_t)((a.w_bytes + 1023) & ~1023u) + s * halo_bytes + 128 + 1024 + 8 * (size_t)a.nblk + 1024; };
   while (stages > 2 && smem_for(stages) > 220 * 1024) --stages;
   if (smem_for(stages) > 227 * 1024)
     return fail(CT_ERR_UNSUPPORTED, "conv_halo: weights + halo do not fit in shared memory%s (%ld bytes)", "",
@@ -466,7 +496,7 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
     const cuuint64_t dims[4] = {(cuuint64_t)g.C_in, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
     const cuuint64_t strides[3] = {(cuuint64_t)g.ld_in * 2, (cuuint64_t)g.W * g.ld_in * 2,
                                    (cuuint64_t)g.H * g.W * g.ld_in * 2};
-    const cuuint32_t box[4] = {(cuuint32_t)(a.swz ? g.C_in : 8), (cuuint32_t)a.pw, (cuuint32_t)a.ph, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)(a.swz ? a.swz / 2 : 8), (cuuint32_t)a.pw, (cuuint32_t)a.ph, 1};
     const CUtensorMapSwizzle sw = a.swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                   : a.swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                   : a.swz == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;

@@ -121,7 +121,11 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
-struct __align__(16) DcnEntry { short y0, x0; float ly, lx, m; };   // 16 bytes
+// Per (tap, output pixel) DCNv2 sampling record, built once per CTA: clamped top-left corner as a 32-bit element
+// offset (image base included, channel 0), element strides to the x+1 / y+1 corners (0 when that neighbour is
+// outside the image, so every load address is valid and the loads need no predicate), and the four bilinear
+// weights already multiplied by the modulation mask and zeroed for corners / samples outside the image.
+struct __align__(16) DcnEntry { int off, dxo, dyo, pad; float w00, w01, w10, w11; };   // 32 bytes
 
 __device__ __forceinline__ void blend8(float (&acc)[8], uint4 v, float w) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
@@ -130,6 +134,16 @@ __device__ __forceinline__ void blend8(float (&acc)[8], uint4 v, float w) {
     const float2 f = __bfloat1622float2(h[q]);
     acc[2 * q] = fmaf(w, f.x, acc[2 * q]);
     acc[2 * q + 1] = fmaf(w, f.y, acc[2 * q + 1]);
+  }
+}
+
+__device__ __forceinline__ void scale8(float (&acc)[8], uint4 v, float w) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float2 f = __bfloat1622float2(h[q]);
+    acc[2 * q] = w * f.x;
+    acc[2 * q + 1] = w * f.y;
   }
 }
 
@@ -182,40 +196,59 @@ conv_tc_kernel(const TcArgs a) {
     const int r0 = tid >> 3;               // rows r0 + 32*i, i < TC_NROW
     const uint32_t swz = (uint32_t)((q ^ (r0 & 7)) << 4);
     const int HWo = g.OH * g.OW;
-    int row_img[TC_NROW], row_iy[TC_NROW], row_ix[TC_NROW];   // image base pixel, top-left input coords of the window
+    int row_off[TC_NROW], row_iy[TC_NROW], row_ix[TC_NROW];   // element offset / coords of the window's top-left input pixel
 #pragma unroll
     for (int i = 0; i < TC_NROW; ++i) {
       const int p = m0 + r0 + 32 * i;
       if (p < g.P_out) {
         const int b = p / HWo, r = p - b * HWo;
         const int oy = r / g.OW, ox = r - oy * g.OW;
-        row_img[i] = b * g.H * g.W;
         row_iy[i] = oy * g.stride - g.pad;
         row_ix[i] = ox * g.stride - g.pad;
+        row_off[i] = (b * g.H * g.W + row_iy[i] * g.W + row_ix[i]) * g.ld_in;
       } else {
-        row_img[i] = 0; row_iy[i] = -100000; row_ix[i] = -100000;
+        row_off[i] = 0; row_iy[i] = -100000; row_ix[i] = -100000;
       }
     }
     if (a.a_mode == CT_A_DCN) {
-      // per (tap,row) sampling parameters, computed once per CTA (row = tid, threads 0..127)
+      // per (tap,row) sampling records, computed once per CTA (row = tid, threads 0..127)
       const int p = m0 + tid;
       const bool ok = p < g.P_out && tid < TC_BM;
-      int oy = 0, ox = 0;
-      if (ok) { const int r = p % HWo; oy = r / g.OW; ox = r - oy * g.OW; }
-      const float* omp = a.om + (size_t)(ok ? p : 0) * g.ld_om;
-#pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        DcnEntry e; e.y0 = 0; e.x0 = 0; e.ly = 0.f; e.lx = 0.f; e.m = 0.f;
+      if (tid < TC_BM) {
+        int oy = 0, ox = 0, img = 0;
+        float om[28];
         if (ok) {
-          const float py = (float)(oy - 1 + tap / 3) + __ldg(omp + 2 * tap);
-          const float px = (float)(ox - 1 + tap % 3) + __ldg(omp + 2 * tap + 1);
-          if (py > -1.f && py < (float)g.H && px > -1.f && px < (float)g.W) {
-            const float y0f = floorf(py), x0f = floorf(px);
-            e.y0 = (short)(int)y0f; e.x0 = (short)(int)x0f;
-            e.ly = py - y0f; e.lx = px - x0f; e.m = __ldg(omp + 18 + tap);
+          const int bb = p / HWo, r = p - bb * HWo;
+          oy = r / g.OW; ox = r - oy * g.OW; img = bb * g.H * g.W;
+          const float4* omp = reinterpret_cast<const float4*>(a.om + (size_t)p * g.ld_om);
+#pragma unroll
+          for (int j = 0; j < 7; ++j) {
+            const float4 t = __ldg(omp + j);
+            om[4 * j] = t.x; om[4 * j + 1] = t.y; om[4 * j + 2] = t.z; om[4 * j + 3] = t.w;
           }
         }
-        if (tid < TC_BM) dcn_tab[tap * TC_BM + tid] = e;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          DcnEntry e; e.off = 0; e.dxo = 0; e.dyo = 0; e.pad = 0; e.w00 = e.w01 = e.w10 = e.w11 = 0.f;
+          if (ok) {
+            const float py = (float)(oy - 1 + tap / 3) + om[2 * tap];
+            const float px = (float)(ox - 1 + tap % 3) + om[2 * tap + 1];
+            if (py > -1.f && py < (float)g.H && px > -1.f && px < (float)g.W) {
+              const float y0f = floorf(py), x0f = floorf(px);
+              const int y0 = (int)y0f, x0 = (int)x0f;
+              const float ly = py - y0f, lx = px - x0f, hy = 1.f - ly, hx = 1.f - lx, m = om[18 + tap];
+              const bool y0ok = y0 >= 0, y1ok = y0 + 1 <= g.H - 1, x0ok = x0 >= 0, x1ok = x0 + 1 <= g.W - 1;
+              e.off = (img + max(y0, 0) * g.W + max(x0, 0)) * g.ld_in;
+              e.dxo = (x0ok && x1ok) ? g.ld_in : 0;
+              e.dyo = (y0ok && y1ok) ? g.W * g.ld_in : 0;
+              e.w00 = (y0ok && x0ok) ? hy * hx * m : 0.f;
+              e.w01 = (y0ok && x1ok) ? hy * lx * m : 0.f;
+              e.w10 = (y1ok && x0ok) ? ly * hx * m : 0.f;
+              e.w11 = (y1ok && x1ok) ? ly * lx * m : 0.f;
+            }
+          }
+          dcn_tab[tap * TC_BM + tid] = e;
+        }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
@@ -240,53 +273,43 @@ conv_tc_kernel(const TcArgs a) {
         for (int i = 0; i < TC_NROW; ++i) sts16(dst + i * 4096u, make_uint4(0, 0, 0, 0));
       } else if (a.a_mode == CT_A_CONV) {
         const int ky = tap / g.KW, kx = tap - ky * g.KW;
+        const int tap_off = (ky * g.W + kx) * g.ld_in + c;      // same for every row of the slice
         uint4 v[TC_NROW];
 #pragma unroll
         for (int i = 0; i < TC_NROW; ++i) {
-          const int iy = row_iy[i] + ky, ix = row_ix[i] + kx;
           v[i] = make_uint4(0, 0, 0, 0);
-          if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
-            v[i] = ldg_nc16(a.x + ((size_t)(row_img[i] + iy * g.W + ix)) * g.ld_in + c);
+          if ((unsigned)(row_iy[i] + ky) < (unsigned)g.H && (unsigned)(row_ix[i] + kx) < (unsigned)g.W)
+            v[i] = ldg_nc16(a.x + (row_off[i] + tap_off));
         }
 #pragma unroll
         for (int i = 0; i < TC_NROW; ++i) sts16(dst + i * 4096u, v[i]);
       } else {
-        // 4 rows x 4 bilinear corners = 16 independent 16-byte loads in flight per thread before any
-        // blend: the gather is latency-bound, memory-level parallelism is what buys throughput here.
+        // 4 rows x 4 bilinear corners = 16 independent, unpredicated 16-byte loads in flight per thread before
+        // any blend (latency-bound gather: memory-level parallelism first), then ~20 instructions per corner.
         const DcnEntry* tab = dcn_tab + tap * TC_BM + r0;
-        const uint4 zero4 = make_uint4(0, 0, 0, 0);
-        {
-          DcnEntry e[TC_NROW];
-          uint4 v[TC_NROW][4];
+        DcnEntry e[TC_NROW];
+        uint4 v[TC_NROW][4];
 #pragma unroll
-          for (int j = 0; j < TC_NROW; ++j) {
-            e[j] = tab[32 * j];
-            const int y0 = e[j].y0, x0 = e[j].x0;
-            const bool live = e[j].m != 0.f;
-            const bool y0ok = live && y0 >= 0, y1ok = live && y0 + 1 <= g.H - 1;
-            const bool x0ok = x0 >= 0, x1ok = x0 + 1 <= g.W - 1;
-            const __nv_bfloat16* base = a.x + ((ptrdiff_t)(row_img[j] + y0 * g.W + x0)) * g.ld_in + c;
-            v[j][0] = (y0ok && x0ok) ? ldg_nc16(base) : zero4;
-            v[j][1] = (y0ok && x1ok) ? ldg_nc16(base + g.ld_in) : zero4;
-            v[j][2] = (y1ok && x0ok) ? ldg_nc16(base + (ptrdiff_t)g.W * g.ld_in) : zero4;
-            v[j][3] = (y1ok && x1ok) ? ldg_nc16(base + (ptrdiff_t)(g.W + 1) * g.ld_in) : zero4;
-          }
+        for (int j = 0; j < TC_NROW; ++j) {
+          e[j] = tab[32 * j];
+          const __nv_bfloat16* p00 = a.x + (e[j].off + c);
+          v[j][0] = ldg_nc16(p00);
+          v[j][1] = ldg_nc16(p00 + e[j].dxo);
+          v[j][2] = ldg_nc16(p00 + e[j].dyo);
+          v[j][3] = ldg_nc16(p00 + e[j].dyo + e[j].dxo);
+        }
 #pragma unroll
-          for (int j = 0; j < TC_NROW; ++j) {
-            const float hy = 1.f - e[j].ly, hx = 1.f - e[j].lx, m = e[j].m;
-            float acc[8];
+        for (int j = 0; j < TC_NROW; ++j) {
+          float acc[8];
+          scale8(acc, v[j][0], e[j].w00);
+          blend8(acc, v[j][1], e[j].w01);
+          blend8(acc, v[j][2], e[j].w10);
+          blend8(acc, v[j][3], e[j].w11);
+          uint4 o;
+          __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-            blend8(acc, v[j][0], hy * hx * m);
-            blend8(acc, v[j][1], hy * e[j].lx * m);
-            blend8(acc, v[j][2], e[j].ly * hx * m);
-            blend8(acc, v[j][3], e[j].ly * e[j].lx * m);
-            uint4 o;
-            __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) oh[q] = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
-            sts16(dst + j * 4096u, o);
-          }
+          for (int q = 0; q < 4; ++q) oh[q] = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
+          sts16(dst + j * 4096u, o);
         }
       }
       fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
@@ -411,7 +434,8 @@ int conv_forward_tc(const ct_conv_desc* d, cudaStream_t st) {
   } else if (d->residual) {
     return fail(CT_ERR_INVALID, "conv_tc: residual unsupported for fp32 outputs%s", "");
   }
-  if (g.H > 32767 || g.W > 32767) return fail(CT_ERR_INVALID, "conv_tc: image too large%s", "");
+  if ((long long)g.B * g.H * g.W * g.ld_in >= (1ll << 31))
+    return fail(CT_ERR_INVALID, "conv_tc: input tensor exceeds 2^31 elements (32-bit offsets)%s", "");
   a.x = (const __nv_bfloat16*)d->x;
   a.w = (const __nv_bfloat16*)d->w;
   a.shift = d->shift;

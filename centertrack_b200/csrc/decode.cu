@@ -16,6 +16,7 @@ namespace ctb {
 
 constexpr int DT = 512;          // threads per CTA
 constexpr int MAXK = 512;
+constexpr int PEAK_CAP = 4096;   // compact list of kept positive peaks (indices), 16 KB
 
 struct DecodeArgs {
   ct_decode_desc d;
@@ -136,6 +137,7 @@ decode_kernel(DecodeArgs a) {
   __shared__ SelState ss;
   __shared__ unsigned long long sel[MAXK];
   __shared__ int sel_n;
+  __shared__ int peak_n;
   __shared__ int is_last;
 
   const ct_decode_desc& d = a.d;
@@ -166,16 +168,51 @@ decode_kernel(DecodeArgs a) {
       const unsigned vb = v > 0.f ? __float_as_uint(v) : 0u;
       return ((unsigned long long)vb << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
     };
-    radix_select(HW, K, keyfn, hist, &ss);
+    // Fast path: after NMS only the kept, positive peaks (~1 element in 10) can enter the top-K.  Compact their
+    // indices once and select over that short list; it is exact whenever there are >= K such peaks (zeros, which
+    // the index-ordered tie rule would otherwise have to rank, are then out of the race).  Degenerate planes
+    // (fewer than K positive peaks, or more than the list holds) take the general path over all H*W keys.
+    unsigned* plist = keep + ((HW + 31) / 32);
+    if (tid == 0) peak_n = 0;
+    __syncthreads();
+    for (int i = tid; i < (HW + DT - 1) / DT * DT; i += DT) {
+      const bool pk = i < HW && ((keep[i >> 5] >> (i & 31)) & 1u) && sp[i] > 0.f;
+      const unsigned m = __ballot_sync(0xffffffffu, pk);
+      if (m) {
+        int base = 0;
+        if ((tid & 31) == 0) base = atomicAdd(&peak_n, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (pk) {
+          const int slot = base + __popc(m & ((1u << (tid & 31)) - 1u));
+          if (slot < PEAK_CAP) plist[slot] = (unsigned)i;
+        }
+      }
+    }
+    __syncthreads();
+    const int npk = peak_n;
+    const bool fast = npk >= K && npk <= PEAK_CAP;
     if (tid == 0) sel_n = 0;
     for (int i = tid; i < a.kpad; i += DT) sel[i] = 0ull;
-    __syncthreads();
-    const unsigned long long prefix = ss.prefix, mask = ss.mask;
-    for (int i = tid; i < HW; i += DT) {
-      const unsigned long long key = keyfn(i);
-      if ((key & mask) >= prefix) {
-        const int slot = atomicAdd(&sel_n, 1);
-        if (slot < MAXK) sel[slot] = key;
+    if (fast) {
+      auto keyfn_l = [&](int j) -> unsigned long long { return keyfn((int)plist[j]); };
+      radix_select(npk, K, keyfn_l, hist, &ss);
+      const unsigned long long prefix = ss.prefix, mask = ss.mask;
+      for (int j = tid; j < npk; j += DT) {
+        const unsigned long long key = keyfn_l(j);
+        if ((key & mask) >= prefix) {
+          const int slot = atomicAdd(&sel_n, 1);
+          if (slot < MAXK) sel[slot] = key;
+        }
+      }
+    } else {
+      radix_select(HW, K, keyfn, hist, &ss);
+      const unsigned long long prefix = ss.prefix, mask = ss.mask;
+      for (int i = tid; i < HW; i += DT) {
+        const unsigned long long key = keyfn(i);
+        if ((key & mask) >= prefix) {
+          const int slot = atomicAdd(&sel_n, 1);
+          if (slot < MAXK) sel[slot] = key;
+        }
       }
     }
     __syncthreads();
@@ -364,7 +401,7 @@ extern "C" int ct_decode(const ct_decode_desc* d, void* stream) {
   while (kpad < d->K) kpad <<= 1;
   a.kpad = kpad;
   const int HW = d->H * d->W, K = d->K, J = a.d.J;
-  size_t smem1 = (size_t)HW * 4 + (size_t)((HW + 31) / 32) * 4;
+  size_t smem1 = (size_t)HW * 4 + (size_t)((HW + 31) / 32) * 4 + (size_t)PEAK_CAP * 4;
   size_t smem2 = (size_t)(7 * K + 4 * J * K) * 4;
   size_t smem = smem1 > smem2 ? smem1 : smem2;
   if (smem > 200 * 1024)

@@ -138,13 +138,15 @@ class DLA34Engine(object):
     engine = self.engine
     n_tile = self._pick_n_tile(P, C_out) if engine == L.CT_ENGINE_TCGEN05 else 0
     if engine == L.CT_ENGINE_TCGEN05 and self.use_halo and a_mode == L.CT_A_CONV and stride == 1 and \
-        (C_in in (16, 32, 48, 64) or (C_in == 8 and sum3)):
-      # thin stride-1 layer: TMA halo tile + descriptor-shifted taps (csrc/conv_halo.cu)
-      nt = 48 if sum3 else min(128, (C_out + 15) // 16 * 16)
+        (C_in in (16, 32, 48, 64, 128, 192, 256) or (C_in == 8 and sum3)):
+      # stride-1 layer whose weights fit in smem: TMA halo tile + descriptor-shifted taps (csrc/conv_halo.cu)
       nblk = k * ((k + 1) // 2) if C_in == 8 else k * k * (C_in // 16)
-      halo = (C_in // 8) * (((8 + k - 1 + (1 if C_in == 8 else 0)) * (16 + k - 1) * 16 + 127) // 128 * 128)
-      if nblk * nt * 32 + 2 * halo <= 216 * 1024:
-        engine, n_tile = L.CT_ENGINE_TCGEN05_HALO, nt
+      halo = C_in * 2 * (8 + k - 1 + (1 if C_in == 8 else 0)) * (16 + k - 1) + 1024 * max(1, C_in // 64)
+      cpad = (C_out + 15) // 16 * 16
+      for nt in ([48] if sum3 else [c for c in (128, 96, 80, 64, 48, 32, 16) if c <= cpad and (c == cpad or cpad % c == 0 or c >= 64)]):
+        if nblk * nt * 32 + 2 * halo + 4096 <= 224 * 1024 and (nt >= 32 or cpad <= 16):
+          engine, n_tile = L.CT_ENGINE_TCGEN05_HALO, nt
+          break
     d = L.ConvDesc()
     d.engine, d.dtype, d.a_mode = engine, self.ct_dtype, a_mode
     d.epilogue_sum3 = sum3

@@ -62,7 +62,7 @@ typedef enum {
   CT_ENGINE_SIMT = 0,          /* fp32 FFMA implicit GEMM (reference accuracy; fp32 or bf16 activations) */
   CT_ENGINE_TCGEN05 = 1,       /* tcgen05 implicit GEMM, A gathered per tap (any stride, DCN) */
   CT_ENGINE_TCGEN05_HALO = 2   /* tcgen05, TMA-loaded halo tile, taps by descriptor shift: stride-1 'same'
-                                  convs with C_in in {8,16,32,48,64} */
+                                  convs with C_in in {8,16,32,48,64,128,192,256} whose weights fit in smem */
 } ct_engine;
 
 /* One convolution-like layer.  Activations are NHWC with an explicit pixel stride (ld, in

@@ -106,7 +106,9 @@ def test_dcn_v2(eng, shape):
 HALO_CASES = [('3x3 64->64 +res', 2, 64, 64, 24, 40, 3, True, 0), ('3x3 16->16', 1, 16, 16, 40, 56, 3, False, 0),
               ('3x3 32->64 ragged tile', 1, 32, 64, 20, 28, 3, False, 0), ('1x1 64->32', 1, 64, 32, 16, 24, 1, False, 0),
               ('3x3 64->1024 8 n-tiles', 1, 64, 1024, 16, 24, 3, False, 128), ('3x3 48->16 odd size', 1, 48, 16, 33, 17, 3, False, 0),
-              ('3x3 64->64 many tiles per CTA', 4, 64, 64, 128, 128, 3, True, 0)]
+              ('3x3 64->64 many tiles per CTA', 4, 64, 64, 128, 128, 3, True, 0),
+              ('3x3 128->128 two 64-ch chunks', 2, 128, 128, 24, 40, 3, True, 32),
+              ('1x1 256->128 four chunks', 1, 256, 128, 16, 24, 1, False, 128), ('3x3 128->64', 1, 128, 64, 20, 28, 3, False, 32)]
 
 
 @pytest.mark.parametrize('case', range(len(HALO_CASES)), ids=[c[0] for c in HALO_CASES])

@@ -92,7 +92,8 @@ def sec_halo(tol=6e-3):
   cases = [('3x3 64->64 res', 2, 64, 64, 24, 40, 3, True, 0), ('3x3 16->16', 1, 16, 16, 40, 56, 3, False, 0),
            ('3x3 32->64', 1, 32, 64, 20, 28, 3, False, 0), ('1x1 64->32', 1, 64, 32, 16, 24, 1, False, 0),
            ('3x3 64->1024 nt128', 1, 64, 1024, 16, 24, 3, False, 128), ('3x3 48->16', 1, 48, 16, 33, 17, 3, False, 0),
-           ('3x3 64->64 big', 4, 64, 64, 128, 128, 3, True, 0)]
+           ('3x3 64->64 big', 4, 64, 64, 128, 128, 3, True, 0), ('3x3 128->128 2 chunks nt32', 2, 128, 128, 24, 40, 3, True, 32),
+           ('1x1 256->128 4 chunks', 1, 256, 128, 16, 24, 1, False, 128), ('3x3 128->64 nt32', 1, 128, 64, 20, 28, 3, False, 32)]
   for (name, B, Cin, Cout, H, W, k, res, nt) in cases:
     x = torch.randn(B, Cin, H, W, generator=g)
     w = torch.randn(Cout, Cin, k, k, generator=g) * (2.0 / (Cin * k * k)) ** 0.5
@@ -127,6 +128,15 @@ def sec_halo(tol=6e-3):
   try:
     got = run_conv(E, D, x.to(dev), w, b, 1, relu=False, out_mode=L.CT_OUT_NCHW_F32, head_act=1, n_tile=80)
     ok &= stat('halo 1x1 64->80 nchw sigmoid', got, ref, 1e-4)
+  except Exception:
+    traceback.print_exc(); ok = False
+  x = torch.randn(2, 256, 16, 24, generator=g)
+  w = torch.randn(80, 256, 1, 1, generator=g) * 0.05
+  b = torch.randn(80, generator=g)
+  ref = torch.sigmoid(F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b))
+  try:
+    got = run_conv(E, D, x.to(dev), w, b, 1, relu=False, out_mode=L.CT_OUT_NCHW_F32, head_act=1, n_tile=80)
+    ok &= stat('halo 1x1 256->80 nchw sigmoid (head)', got, ref, 1e-4)
   except Exception:
     traceback.print_exc(); ok = False
   # stem: 7x7, C_in = 8 (img3, pre3, hm1, 0), block-diagonal 48 outputs, relu per group then sum
