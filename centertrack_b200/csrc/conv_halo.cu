@@ -90,6 +90,19 @@ __device__ __forceinline__ void h_mma(uint32_t tmem_d, uint64_t adesc, uint64_t 
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+__device__ __forceinline__ void h_mma_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.eq.b32 p, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+}
+__device__ __forceinline__ void h_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void h_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -208,7 +221,7 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
     // One thread issues every tcgen05.mma, so its per-instruction overhead IS the MMA rate: all descriptor
     // arithmetic is hoisted into a per-CTA table (A descriptors relative to halo stage 0, one per K=16 block;
     // built once by the whole warp), leaving load + add + issue per MMA.
-    uint2* tabA = reinterpret_cast<uint2*>(sm + off_bar + 128 + 1024);
+    uint4* tab = reinterpret_cast<uint4*>(sm + off_bar + 128 + 1024);   // {A desc (stage 0), B desc} per K=16 block
     {
       const uint32_t a_sbo = (uint32_t)a.pw * 16u;
       const uint32_t a_lbo = a.pair_taps ? 16u : (uint32_t)a.plane_bytes;
@@ -232,15 +245,13 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
           else
             dsc = h_sdesc(sH + (uint32_t)(2 * q) * a.plane_bytes + (uint32_t)(ky * a.pw + kx) * 16u, a_lbo, a_sbo);
         }
-        tabA[blk] = make_uint2((uint32_t)dsc, (uint32_t)(dsc >> 32));
+        const uint64_t bdsc = h_sdesc(sW + (uint32_t)blk * (uint32_t)a.n_tile * 32u, (uint32_t)a.n_tile * 16u, 128u);
+        tab[blk] = make_uint4((uint32_t)dsc, (uint32_t)(dsc >> 32), (uint32_t)bdsc, (uint32_t)(bdsc >> 32));
       }
       __syncwarp();
     }
     if (lane == 0) {
       const uint32_t idesc = h_idesc(a.n_tile);
-      const uint32_t b_lbo = (uint32_t)a.n_tile * 16u, b_sbo = 128u;
-      const uint64_t b_desc0 = h_sdesc(sW, b_lbo, b_sbo);
-      const uint32_t b_step = ((uint32_t)a.n_tile * 32u) >> 4;       // descriptor start-address units (16 B)
       h_mbar_wait(w_full, 0);
       int it = 0;
       for (int sp = sp0; sp < sp_total; sp += sp_stride, ++it) {
@@ -253,13 +264,19 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
         h_fence_after();
         const uint32_t stage_off = (uint32_t)(s * halo_bytes) >> 4;   // stays inside the 14-bit address field
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.n_tile);
-        uint64_t bd = b_desc0;
-#pragma unroll 4
-        for (int blk = 0; blk < a.nblk; ++blk) {
-          const uint2 t = tabA[blk];
-          const uint64_t ad = ((uint64_t)t.y << 32) | (uint64_t)(t.x + stage_off);
-          h_mma(d_tmem, ad, bd, idesc, blk > 0 ? 1u : 0u);
-          bd += b_step;
+        // the first MMA of a tile overwrites the accumulator, the rest accumulate: peel it so the loop body is
+        // load descriptor pair / add stage offset / issue -- the single issuing thread's instruction count per
+        // MMA is what bounds the tensor rate for narrow N tiles
+        {
+          const uint4 t = tab[0];
+          h_mma(d_tmem, ((uint64_t)t.y << 32) | (uint64_t)(t.x + stage_off), ((uint64_t)t.w << 32) | (uint64_t)t.z,
+                idesc, 0u);
+        }
+#pragma unroll 8
+        for (int blk = 1; blk < a.nblk; ++blk) {
+          const uint4 t = tab[blk];
+          h_mma_acc(d_tmem, ((uint64_t)t.y << 32) | (uint64_t)(t.x + stage_off), ((uint64_t)t.w << 32) | (uint64_t)t.z,
+                    idesc);
         }
         h_commit(halo_empty(s));
         h_commit(tmem_full(acc));
@@ -285,38 +302,28 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
       const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * a.n_tile);
       if (a.sum3) {
         // stem: three 16-channel groups, ReLU each (after its folded-BN shift), then sum (dla.py:307-311).
-        // One warp per lane quarter does it (the sum runs across column groups of the same pixel).
-        if (chalf == 0) {
-          float s16[16];
+        // Warp half `chalf` produces output channels 8*chalf .. 8*chalf+7 (columns g*16 + 8*chalf + j).
+        float s8[8];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) s16[j] = 0.f;
+        for (int j = 0; j < 8; ++j) s8[j] = 0.f;
 #pragma unroll
-          for (int grp = 0; grp < 3; ++grp) {
-            uint32_t rr[16];
-            h_ld16(t_lane + grp * 16, rr);
-            if (!((a.sum3 >> grp) & 1)) continue;          // absent input (pre_img / pre_hm is None)
-            const float4* sh4 = reinterpret_cast<const float4*>(s_shift + grp * 16);
+        for (int grp = 0; grp < 3; ++grp) {
+          uint32_t rr[8];
+          h_ld8(t_lane + grp * 16 + chalf * 8, rr);
+          if (!((a.sum3 >> grp) & 1)) continue;          // absent input (pre_img / pre_hm is None)
+          const float4* sh4 = reinterpret_cast<const float4*>(s_shift + grp * 16 + chalf * 8);
+          const float4 sa = sh4[0], sb = sh4[1];
+          s8[0] += fmaxf(__uint_as_float(rr[0]) + sa.x, 0.f); s8[1] += fmaxf(__uint_as_float(rr[1]) + sa.y, 0.f);
+          s8[2] += fmaxf(__uint_as_float(rr[2]) + sa.z, 0.f); s8[3] += fmaxf(__uint_as_float(rr[3]) + sa.w, 0.f);
+          s8[4] += fmaxf(__uint_as_float(rr[4]) + sb.x, 0.f); s8[5] += fmaxf(__uint_as_float(rr[5]) + sb.y, 0.f);
+          s8[6] += fmaxf(__uint_as_float(rr[6]) + sb.z, 0.f); s8[7] += fmaxf(__uint_as_float(rr[7]) + sb.w, 0.f);
+        }
+        if (p_ok) {
+          uint4 o;
+          __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 sh = sh4[j4];
-              s16[4 * j4 + 0] += fmaxf(__uint_as_float(rr[4 * j4 + 0]) + sh.x, 0.f);
-              s16[4 * j4 + 1] += fmaxf(__uint_as_float(rr[4 * j4 + 1]) + sh.y, 0.f);
-              s16[4 * j4 + 2] += fmaxf(__uint_as_float(rr[4 * j4 + 2]) + sh.z, 0.f);
-              s16[4 * j4 + 3] += fmaxf(__uint_as_float(rr[4 * j4 + 3]) + sh.w, 0.f);
-            }
-          }
-          if (p_ok) {
-            uint4 oa, ob;
-            __nv_bfloat162* pa2 = reinterpret_cast<__nv_bfloat162*>(&oa);
-            __nv_bfloat162* pb2 = reinterpret_cast<__nv_bfloat162*>(&ob);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              pa2[j] = __floats2bfloat162_rn(s16[2 * j], s16[2 * j + 1]);
-              pb2[j] = __floats2bfloat162_rn(s16[8 + 2 * j], s16[8 + 2 * j + 1]);
-            }
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + p * g.ld_out);
-            op[0] = oa; op[1] = ob;
-          }
+          for (int j = 0; j < 4; ++j) po[j] = __floats2bfloat162_rn(s8[2 * j], s8[2 * j + 1]);
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + p * g.ld_out + chalf * 8) = o;
         }
       } else {
         for (int col = chalf * 16; col < a.n_tile; col += 32) {
@@ -364,12 +371,16 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
             float* op = reinterpret_cast<float*>(a.out) + p * g.ld_out + o0;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              if (o0 + j < g.C_out) {
-                float t = v[j];
-                if (g.relu) t = fmaxf(t, 0.f);
-                if (o0 + j >= g.sig_from) t = sigmoidf_ref(t);
-                op[j] = t;
-              }
+              if (g.relu) v[j] = fmaxf(v[j], 0.f);
+              if (o0 + j >= g.sig_from) v[j] = sigmoidf_ref(v[j]);
+            }
+            if (o0 + 16 <= g.ld_out && (g.ld_out & 3) == 0) {      // padded row: four 16-byte stores
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4)
+                reinterpret_cast<float4*>(op)[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) if (o0 + j < g.C_out) op[j] = v[j];
             }
           } else {
             float* op = reinterpret_cast<float*>(a.out) + ((size_t)b * g.C_out + o0) * HWo + (size_t)oy * g.OW + ox;
@@ -472,7 +483,7 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
   a.tmem_cols = cols;
   const size_t halo_bytes = (size_t)a.planes * a.plane_bytes;
   int stages = 3;
-  auto smem_for = [&](int s) { return (size_t)((a.w_bytes + 1023) & ~1023u) + s * halo_bytes + 128 + 1024 + 8 * (size_t)a.nblk + 1024; };
+  auto smem_for = [&](int s) { return (size_t)((a.w_bytes + 1023) & ~1023u) + s * halo_bytes + 128 + 1024 + 16 * (size_t)a.nblk + 1024; };
   while (stages > 2 && smem_for(stages) > 220 * 1024) --stages;
   if (smem_for(stages) > 227 * 1024)
     return fail(CT_ERR_UNSUPPORTED, "conv_halo: weights + halo do not fit in shared memory%s (%ld bytes)", "",
@@ -518,7 +529,7 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
   const int by_tmem = 512 / cols;
   if (per_sm > by_tmem) per_sm = by_tmem;
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 4) per_sm = 4;
+  if (per_sm > 2) per_sm = 2;       // register file: 2 x 320 threads x 81 registers
   long want = (long)sms * per_sm;
   long groups = want / a.n_tiles_n;
   if (groups < 1) groups = 1;

@@ -366,12 +366,16 @@ conv_tc_kernel(const TcArgs a) {
         float* op = reinterpret_cast<float*>(a.out) + (size_t)p * g.ld_out + o0;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          if (o0 + j < g.C_out) {
-            float t = v[j];
-            if (g.relu) t = fmaxf(t, 0.f);
-            if (o0 + j >= g.sig_from) t = sigmoidf_ref(t);
-            op[j] = t;
-          }
+          if (g.relu) v[j] = fmaxf(v[j], 0.f);
+          if (o0 + j >= g.sig_from) v[j] = sigmoidf_ref(v[j]);
+        }
+        if (o0 + 16 <= g.ld_out && (g.ld_out & 3) == 0) {      // padded row: four 16-byte stores
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4)
+            reinterpret_cast<float4*>(op)[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (o0 + j < g.C_out) op[j] = v[j];
         }
       } else {
         const int b = p / HWo, rr = p - b * HWo;
