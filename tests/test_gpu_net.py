@@ -201,8 +201,9 @@ def test_e2e_512_process_matches_reference_golden(precision, golden_dir):
     gi = {v: i for i, v in enumerate(got_inds[0].tolist())}
     r_idx = np.array([ri[v] for v in common]); g_idx = np.array([gi[v] for v in common])
     assert np.abs(dets['scores'][0][g_idx] - g['det.scores'][0][r_idx]).max() < 1e-3
-    assert np.abs(dets['bboxes'][0][g_idx] - g['det.bboxes'][0][r_idx]).max() < 5e-3
-    assert np.abs(dets['tracking'][0][g_idx] - g['det.tracking'][0][r_idx]).max() < 5e-3
+    # regression maps of this model reach |v| ~ 8: 1e-3 x scale
+    assert np.abs(dets['bboxes'][0][g_idx] - g['det.bboxes'][0][r_idx]).max() < 1e-2
+    assert np.abs(dets['tracking'][0][g_idx] - g['det.tracking'][0][r_idx]).max() < 1e-2
   else:
     # detections of the bf16 path on a chaotic random-weight network: most of the reference's top-100 survive
     overlap = len(set(ref_inds[0].tolist()) & set(got_inds[0].tolist())) / 100.0
