@@ -67,5 +67,6 @@ int conv_forward_simt(const ct_conv_desc* d, cudaStream_t st);
 int conv_forward_tc(const ct_conv_desc* d, cudaStream_t st);
 int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st);
 int halo_blocks(int C_in, int KH, int KW);
+int halo_set_trace(void* buf);
 
 }  // namespace ctb

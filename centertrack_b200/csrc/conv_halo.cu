@@ -25,6 +25,15 @@
 namespace ctb {
 
 constexpr int HT_W = 8, HT_H = 16;       // output tile (x, y)
+
+// Optional timeline trace of CTA 0 (ct_debug_trace): 8 clock64() stamps per work item --
+// 0 producer acquired the halo stage, 1 TMA issued, 2 MMA saw the halo, 3 MMA got a free accumulator,
+// 4 MMAs issued + committed, 5 epilogue saw the accumulator, 6 epilogue released it.  Off (nullptr) by default.
+__device__ unsigned long long* g_halo_trace = nullptr;
+__device__ __forceinline__ void h_stamp(int it, int k) {
+  unsigned long long* t = g_halo_trace;
+  if (t != nullptr && blockIdx.x == 0 && it < 256) t[it * 8 + k] = (unsigned long long)clock64();
+}
 constexpr int H_THREADS = 320;           // 8 epilogue warps + TMA warp + MMA warp
 constexpr int H_EPI_WARPS = 8;
 
@@ -202,6 +211,7 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
         const int s = it % S;
         const uint32_t ph = (uint32_t)(it / S) & 1u;
         h_mbar_wait(halo_empty(s), ph ^ 1u);
+        h_stamp(it, 0);
         const int b = sp / per_img, r = sp - b * per_img;
         const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
         const int x0 = tx * HT_W - g.pad, y0 = ty * HT_H - g.pad;
@@ -214,6 +224,7 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
           for (int p = 0; p < a.planes; ++p)
             h_tma_4d(sH + s * halo_bytes + p * a.plane_bytes, &tmap, p * cstep, x0, y0, b, halo_full(s));
         }
+        h_stamp(it, 1);
       }
     }
   } else if (warp == 9) {
@@ -260,7 +271,9 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
         const int acc = it & 1;
         const uint32_t pa = (uint32_t)(it >> 1) & 1u;
         h_mbar_wait(halo_full(s), ph);
+        h_stamp(it, 2);
         h_mbar_wait(tmem_empty(acc), pa ^ 1u);
+        h_stamp(it, 3);
         h_fence_after();
         const uint32_t stage_off = (uint32_t)(s * halo_bytes) >> 4;   // stays inside the 14-bit address field
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.n_tile);
@@ -280,6 +293,7 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
         }
         h_commit(halo_empty(s));
         h_commit(tmem_full(acc));
+        h_stamp(it, 4);
       }
     }
   } else {
@@ -288,6 +302,29 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
     const int row = wq * 32 + lane;              // GEMM row = g*8 + r  ->  pixel (ty*16 + g, tx*8 + r)
     const int gy = row >> 3, rx = row & 7;
     const int HWo = g.OH * g.OW;
+    // Residual tiles are prefetched one work item ahead into registers (the load does not depend on the MMA):
+    // issued right after the previous item consumed its copy, they land while this warp waits for the next
+    // accumulator -- otherwise every item pays a full L2/HBM round trip inside the serial epilogue chain.
+    constexpr int PF = 4;                      // 16-column chunks per warp that can be prefetched (n_tile <= 128)
+    uint4 rq[PF][2];
+    const bool use_res = a.residual != nullptr && g.out_mode == CT_OUT_NHWC && !a.sum3;
+    auto prefetch_residual = [&](int sp_n) {
+      const int bn = sp_n / per_img, rn = sp_n - bn * per_img;
+      const int tyn = rn / a.tiles_x, txn = rn - tyn * a.tiles_x;
+      const int oyn = tyn * HT_H + gy, oxn = txn * HT_W + rx;
+      const bool okn = oyn < g.OH && oxn < g.OW;
+      const size_t pn = ((size_t)bn * g.OH + oyn) * g.OW + oxn;
+#pragma unroll
+      for (int i = 0; i < PF; ++i) {
+        const int col = chalf * 16 + 32 * i;
+        rq[i][0] = make_uint4(0, 0, 0, 0); rq[i][1] = make_uint4(0, 0, 0, 0);
+        if (okn && col < a.n_tile && n0 + col < g.C_out) {
+          const uint4* rp = reinterpret_cast<const uint4*>(a.residual + pn * g.ld_res + n0 + col);
+          rq[i][0] = __ldg(rp); rq[i][1] = __ldg(rp + 1);
+        }
+      }
+    };
+    if (use_res && sp0 < sp_total) prefetch_residual(sp0);
     int it = 0;
     for (int sp = sp0; sp < sp_total; sp += sp_stride, ++it) {
       const int acc = it & 1;
@@ -298,6 +335,7 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
       const bool p_ok = oy < g.OH && ox < g.OW;
       const size_t p = ((size_t)b * g.OH + oy) * g.OW + ox;
       h_mbar_wait(tmem_full(acc), pa);
+      if (tid == 0) h_stamp(it, 5);
       h_fence_after();
       const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * a.n_tile);
       if (a.sum3) {
@@ -343,8 +381,16 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
           }
           if (g.out_mode == CT_OUT_NHWC) {
             if (a.residual) {
-              const uint4* rp = reinterpret_cast<const uint4*>(a.residual + p * g.ld_res + o0);
-              const uint4 ra = __ldg(rp), rb = __ldg(rp + 1);
+              uint4 ra, rb;
+              const int ci = col >> 5;                     // this warp's chunk index
+              if (ci < PF) {
+                ra = rq[0][0]; rb = rq[0][1];
+#pragma unroll
+                for (int i = 1; i < PF; ++i) if (ci == i) { ra = rq[i][0]; rb = rq[i][1]; }
+              } else {
+                const uint4* rp = reinterpret_cast<const uint4*>(a.residual + p * g.ld_res + o0);
+                ra = __ldg(rp); rb = __ldg(rp + 1);
+              }
               const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&ra);
               const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&rb);
 #pragma unroll
@@ -395,8 +441,10 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
           }
         }
       }
+      if (use_res && sp + sp_stride < sp_total) prefetch_residual(sp + sp_stride);
       h_fence_before();
       h_mbar_arrive(tmem_empty(acc));      // all epilogue threads arrive: frees this accumulator stage
+      if (tid == 0) h_stamp(it, 6);
     }
   }
 
@@ -424,6 +472,11 @@ static EncodeTiledFn get_encode() {
     return nullptr;
   fn = reinterpret_cast<EncodeTiledFn>(p);
   return fn;
+}
+
+int halo_set_trace(void* buf) {
+  unsigned long long* p = (unsigned long long*)buf;
+  return cudaMemcpyToSymbol(g_halo_trace, &p, sizeof(p)) == cudaSuccess ? CT_OK : CT_ERR_CUDA;
 }
 
 int halo_blocks(int C_in, int KH, int KW) {

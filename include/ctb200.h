@@ -195,6 +195,9 @@ int ct_abi_version(void);
 /* Kernels launched by this library on the calling thread since the last reset. */
 int64_t ct_launch_count(void);
 void ct_reset_launch_count(void);
+/* Debug: timeline trace of CTA 0 of the halo conv kernel into device_buf (>= 16 KB of uint64: 8 clock64()
+ * stamps per work item, see csrc/conv_halo.cu); NULL switches it off (default). */
+int ct_debug_trace(void* device_buf);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,46 @@
+"""Timeline of CTA 0 of the halo conv kernel for a few layer shapes (B=16): python tools/halo_trace.py"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+from centertrack_b200 import _lib as L       # noqa
+from gpu_helpers import run_conv             # noqa
+
+lib = L.lib()
+cases = [('heads.0 64->1024 nt128 128x128', 16, 64, 1024, 128, 128, 3, False, 128),
+         ('level2 64->64 +res 128x128', 16, 64, 64, 128, 128, 3, True, 64),
+         ('level3 128->128 +res nt32 64x64', 16, 128, 128, 64, 64, 3, True, 32),
+         ('offset 64->27 nt32 128x128', 16, 64, 32, 128, 128, 3, False, 32),
+         ('level0 16->16 512x512', 16, 16, 16, 512, 512, 3, False, 16)]
+g = torch.Generator().manual_seed(0)
+for (name, B, Cin, Cout, H, W, k, res, nt) in cases:
+  x = torch.randn(B, Cin, H, W, generator=g)
+  w = torch.randn(Cout, Cin, k, k, generator=g) * 0.05
+  b = torch.zeros(Cout)
+  r = torch.randn(B, Cout, H, W, generator=g).cuda() if res else None
+  tr = torch.zeros(256 * 8, dtype=torch.int64, device='cuda')
+  run_conv(L.CT_ENGINE_TCGEN05_HALO, L.CT_BF16, x.cuda(), w, b, 1, True, r, n_tile=nt)     # warm
+  L.check(lib.ct_debug_trace(C.c_void_p(tr.data_ptr())))
+  run_conv(L.CT_ENGINE_TCGEN05_HALO, L.CT_BF16, x.cuda(), w, b, 1, True, r, n_tile=nt)
+  torch.cuda.synchronize()
+  L.check(lib.ct_debug_trace(None))
+  t = tr.cpu().numpy().reshape(256, 8).astype(np.int64)
+  n = int((t[:, 4] > 0).sum())
+  t0 = t[0, 0]
+  print('==== %s : %d items in CTA 0' % (name, n))
+  print('  it   prod_acq  tma_iss | mma_halo mma_acc  mma_done | epi_start epi_done   (cycles since start; item period)')
+  for i in list(range(min(n, 6))) + list(range(max(6, n - 3), n)):
+    row = t[i] - t0
+    per = (t[i, 4] - t[i - 1, 4]) if i > 0 else 0
+    print('  %3d %9d %8d | %8d %8d %8d | %8d %8d   period %d' % (i, row[0], row[1], row[2], row[3], row[4], row[5], row[6], per))
+  if n > 4:
+    d = t[2:n]
+    print('  mean over items 2..: wait_halo %.0f  wait_acc %.0f  issue %.0f  | epi %.0f | tma_latency(iss->mma_halo of same item) %.0f  period %.0f' % (
+        np.mean(d[:, 2] - np.maximum(t[1:n - 1, 4], d[:, 2] * 0 + t[1:n - 1, 4])), np.mean(d[:, 3] - d[:, 2]), np.mean(d[:, 4] - d[:, 3]),
+        np.mean(d[:, 6] - d[:, 5]), np.mean(d[:, 2] - d[:, 1]), np.mean(np.diff(t[1:n, 4]))))
