@@ -52,6 +52,9 @@ struct HaloArgs {
   int merged_xc;                        // 1: 3-D tensor map with (x, c) merged (C_in == ld_in == 8)
   int sum3;                             // != 0: stem epilogue sum_g relu(group g + shift) -> 16 ch; bit g = group present
   uint32_t w_bytes;                     // bytes of one n-tile's weights
+  // A-descriptor walk of one work item (all in 16-byte units, warp-uniform): for ky, kx|pair, chunk, kstep
+  int m_nky, m_nkx, m_nc, m_nq;
+  uint32_t m_sky, m_skx, m_sc, m_sq, m_alo, m_ahi;
 };
 
 // ---- PTX (same wrappers as conv_tc.cu; kept local so each TU is self-contained) ----
@@ -229,41 +232,17 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
     }
   } else if (warp == 9) {
     // ===================== MMA issuer =====================
-    // One thread issues every tcgen05.mma, so its per-instruction overhead IS the MMA rate: all descriptor
-    // arithmetic is hoisted into a per-CTA table (A descriptors relative to halo stage 0, one per K=16 block;
-    // built once by the whole warp), leaving load + add + issue per MMA.
-    uint4* tab = reinterpret_cast<uint4*>(sm + off_bar + 128 + 1024);   // {A desc (stage 0), B desc} per K=16 block
+    // The whole warp runs this loop CONVERGENTLY and only the tcgen05.mma / commit statements are predicated on
+    // the leader lane: the descriptors are then warp-uniform arithmetic on kernel parameters and loop counters,
+    // which the compiler keeps in uniform registers.  (Issuing from a divergent `if (lane == 0)` region, or reading
+    // descriptors from a shared-memory table, costs several R2UR moves per UTCHMMA: ~100 cycles per MMA.)
+    const bool leader = lane == 0;
+    const uint32_t idesc = h_idesc(a.n_tile);
+    const uint32_t b_hi = (uint32_t)(h_sdesc(0, (uint32_t)a.n_tile * 16u, 128u) >> 32);
+    const uint32_t b_lo0 = (uint32_t)h_sdesc(sW, (uint32_t)a.n_tile * 16u, 128u);
+    const uint32_t b_step = ((uint32_t)a.n_tile * 32u) >> 4;          // descriptor start-address units (16 B)
+    h_mbar_wait(w_full, 0);
     {
-      const uint32_t a_sbo = (uint32_t)a.pw * 16u;
-      const uint32_t a_lbo = a.pair_taps ? 16u : (uint32_t)a.plane_bytes;
-      const int qn = a.pair_taps ? 1 : (g.C_in >> 4);
-      const int pairs = (g.KW + 1) >> 1;
-      for (int blk = lane; blk < a.nblk; blk += 32) {
-        uint64_t dsc;
-        if (a.pair_taps) {
-          const int ky = blk / pairs, kp = blk - ky * pairs;
-          dsc = h_sdesc(sH + (uint32_t)(ky * a.pw + 2 * kp) * 16u, a_lbo, a_sbo);
-        } else {
-          const int tap = blk / qn, q = blk - tap * qn;
-          const int ky = tap / g.KW, kx = tap - ky * g.KW;
-          if (a.swz) {      // q-th 16-channel step: chunk (q*16)/(channels per row), 32-byte K step inside the row
-            const int per_row = a.swz >> 5;                       // K=16 steps per row (1, 2 or 4)
-            const int chunk = q / per_row, qq = q - chunk * per_row;
-            dsc = h_sdesc_swz(sH + (uint32_t)chunk * a.plane_bytes + (uint32_t)(ky * a.pw + kx) * (uint32_t)a.swz +
-                                  (uint32_t)qq * 32u,
-                              (uint32_t)a.pw * (uint32_t)a.swz, a.swz, a.use_base_offset);
-          }
-          else
-            dsc = h_sdesc(sH + (uint32_t)(2 * q) * a.plane_bytes + (uint32_t)(ky * a.pw + kx) * 16u, a_lbo, a_sbo);
-        }
-        const uint64_t bdsc = h_sdesc(sW + (uint32_t)blk * (uint32_t)a.n_tile * 32u, (uint32_t)a.n_tile * 16u, 128u);
-        tab[blk] = make_uint4((uint32_t)dsc, (uint32_t)(dsc >> 32), (uint32_t)bdsc, (uint32_t)(bdsc >> 32));
-      }
-      __syncwarp();
-    }
-    if (lane == 0) {
-      const uint32_t idesc = h_idesc(a.n_tile);
-      h_mbar_wait(w_full, 0);
       int it = 0;
       for (int sp = sp0; sp < sp_total; sp += sp_stride, ++it) {
         const int s = it % S;
@@ -271,29 +250,35 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
         const int acc = it & 1;
         const uint32_t pa = (uint32_t)(it >> 1) & 1u;
         h_mbar_wait(halo_full(s), ph);
-        h_stamp(it, 2);
+        if (leader) h_stamp(it, 2);
         h_mbar_wait(tmem_empty(acc), pa ^ 1u);
-        h_stamp(it, 3);
+        if (leader) h_stamp(it, 3);
         h_fence_after();
-        const uint32_t stage_off = (uint32_t)(s * halo_bytes) >> 4;   // stays inside the 14-bit address field
+        const uint32_t base16 = a.m_alo + ((sH + (uint32_t)s * halo_bytes) >> 4);   // start address stays < 2^14
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.n_tile);
-        // the first MMA of a tile overwrites the accumulator, the rest accumulate: peel it so the loop body is
-        // load descriptor pair / add stage offset / issue -- the single issuing thread's instruction count per
-        // MMA is what bounds the tensor rate for narrow N tiles
-        {
-          const uint4 t = tab[0];
-          h_mma(d_tmem, ((uint64_t)t.y << 32) | (uint64_t)(t.x + stage_off), ((uint64_t)t.w << 32) | (uint64_t)t.z,
-                idesc, 0u);
+        uint32_t b_lo = b_lo0;
+        uint32_t accum = 0;
+        for (int ky = 0; ky < a.m_nky; ++ky) {
+          for (int kx = 0; kx < a.m_nkx; ++kx) {
+            const uint32_t tap16 = base16 + (uint32_t)ky * a.m_sky + (uint32_t)kx * a.m_skx;
+            for (int c = 0; c < a.m_nc; ++c) {
+              for (int q = 0; q < a.m_nq; ++q) {
+                const uint32_t a_lo = tap16 + (uint32_t)c * a.m_sc + (uint32_t)q * a.m_sq;
+                if (leader)
+                  h_mma(d_tmem, ((uint64_t)a.m_ahi << 32) | (uint64_t)a_lo, ((uint64_t)b_hi << 32) | (uint64_t)b_lo,
+                        idesc, accum);
+                accum = 1;
+                b_lo += b_step;
+              }
+            }
+          }
         }
-#pragma unroll 8
-        for (int blk = 1; blk < a.nblk; ++blk) {
-          const uint4 t = tab[blk];
-          h_mma_acc(d_tmem, ((uint64_t)t.y << 32) | (uint64_t)(t.x + stage_off), ((uint64_t)t.w << 32) | (uint64_t)t.z,
-                    idesc);
+        if (leader) {
+          h_commit(halo_empty(s));
+          h_commit(tmem_full(acc));
+          h_stamp(it, 4);
         }
-        h_commit(halo_empty(s));
-        h_commit(tmem_full(acc));
-        h_stamp(it, 4);
+        __syncwarp();
       }
     }
   } else {
@@ -527,6 +512,24 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
   a.box_bytes = a.pw * a.ph * (a.swz ? a.swz : 16);
   a.plane_bytes = (a.box_bytes + 1023) / 1024 * 1024;
   a.w_bytes = (uint32_t)a.nblk * n_tile * 32u;
+  if (a.pair_taps) {                 // one MMA = taps (ky, 2kp) and (ky, 2kp+1): K-core 1 is the next pixel
+    a.m_nky = g.KH; a.m_nkx = (g.KW + 1) / 2; a.m_nc = 1; a.m_nq = 1;
+    a.m_sky = a.pw; a.m_skx = 2; a.m_sc = 0; a.m_sq = 0;
+    a.m_alo = 1u << 16;                                   // LBO = 16 B
+    a.m_ahi = (uint32_t)a.pw | (1u << 14);                // SBO = pw*16 B, version 1
+  } else if (a.swz) {
+    const uint32_t rb16 = (uint32_t)a.swz >> 4;
+    a.m_nky = g.KH; a.m_nkx = g.KW; a.m_nc = a.planes; a.m_nq = (g.C_in < 64 ? g.C_in : 64) / 16;
+    a.m_sky = (uint32_t)a.pw * rb16; a.m_skx = rb16; a.m_sc = (uint32_t)a.plane_bytes >> 4; a.m_sq = 2;
+    a.m_alo = 1u << 16;
+    const uint32_t layout = a.swz == 128 ? 2u : (a.swz == 64 ? 4u : 6u);
+    a.m_ahi = ((uint32_t)a.pw * rb16) | (1u << 14) | (layout << 29);
+  } else {
+    a.m_nky = g.KH; a.m_nkx = g.KW; a.m_nc = 1; a.m_nq = g.C_in / 16;
+    a.m_sky = a.pw; a.m_skx = 1; a.m_sc = 0; a.m_sq = 2u * ((uint32_t)a.plane_bytes >> 4);
+    a.m_alo = ((uint32_t)a.plane_bytes >> 4) << 16;       // LBO = plane stride
+    a.m_ahi = (uint32_t)a.pw | (1u << 14);
+  }
   a.tiles_x = (g.OW + HT_W - 1) / HT_W;
   a.tiles_y = (g.OH + HT_H - 1) / HT_H;
   a.tiles_total = g.B * a.tiles_x * a.tiles_y;
@@ -536,7 +539,7 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
   a.tmem_cols = cols;
   const size_t halo_bytes = (size_t)a.planes * a.plane_bytes;
   int stages = 3;
-  auto smem_for = [&](int s) { return (size_t)((a.w_bytes + 1023) & ~1023u) + s * halo_bytes + 128 + 1024 + 16 * (size_t)a.nblk + 1024; };
+  auto smem_for = [&](int s) { return (size_t)((a.w_bytes + 1023) & ~1023u) + s * halo_bytes + 128 + 1024 + 1024; };
   while (stages > 2 && smem_for(stages) > 220 * 1024) --stages;
   if (smem_for(stages) > 227 * 1024)
     return fail(CT_ERR_UNSUPPORTED, "conv_halo: weights + halo do not fit in shared memory%s (%ld bytes)", "",

@@ -17,7 +17,12 @@ cases = [('heads.0 64->1024 nt128 128x128', 16, 64, 1024, 128, 128, 3, False, 12
          ('level2 64->64 +res 128x128', 16, 64, 64, 128, 128, 3, True, 64),
          ('level3 128->128 +res nt32 64x64', 16, 128, 128, 64, 64, 3, True, 32),
          ('offset 64->27 nt32 128x128', 16, 64, 32, 128, 128, 3, False, 32),
-         ('level0 16->16 512x512', 16, 16, 16, 512, 512, 3, False, 16)]
+         ('level0 16->16 512x512', 16, 16, 16, 512, 512, 3, False, 16),
+         ('1x1 64->64 (canonical SBO=1024) 128x128', 16, 64, 64, 128, 128, 1, False, 64),
+         ('1x1 64->128 128x128', 16, 64, 128, 128, 128, 1, False, 128),
+         ('1x1 256->128 4 chunks 128x128', 16, 256, 128, 128, 128, 1, False, 128),
+         ('5x5 64->64 (100 MMAs/item) 128x128', 16, 64, 64, 128, 128, 5, False, 64),
+         ('5x5 64->16 128x128', 16, 64, 16, 128, 128, 5, False, 16)]
 g = torch.Generator().manual_seed(0)
 for (name, B, Cin, Cout, H, W, k, res, nt) in cases:
   x = torch.randn(B, Cin, H, W, generator=g)
@@ -39,6 +44,9 @@ for (name, B, Cin, Cout, H, W, k, res, nt) in cases:
     row = t[i] - t0
     per = (t[i, 4] - t[i - 1, 4]) if i > 0 else 0
     print('  %3d %9d %8d | %8d %8d %8d | %8d %8d   period %d' % (i, row[0], row[1], row[2], row[3], row[4], row[5], row[6], per))
+  nblk = (k * k * (Cin // 16))
+  if n > 4:
+    print('  issue phase per MMA: %.0f cycles (nblk %d); period per MMA %.0f' % (np.mean(t[2:n, 4] - t[2:n, 3]) / nblk, nblk, np.mean(np.diff(t[1:n, 4])) / nblk))
   if n > 4:
     d = t[2:n]
     print('  mean over items 2..: wait_halo %.0f  wait_acc %.0f  issue %.0f  | epi %.0f | tma_latency(iss->mma_halo of same item) %.0f  period %.0f' % (
