@@ -102,6 +102,24 @@ __device__ __forceinline__ void h_mma(uint32_t tmem_d, uint64_t adesc, uint64_t 
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+// Issued by ALL lanes of the (converged) MMA warp: elect.sync picks one lane and predicates the instruction, so
+// there is no divergent branch around the UTCHMMA and its operands stay warp-uniform (cute::elect_one_sync idiom).
+__device__ __forceinline__ void h_mma_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pa;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void h_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void h_mma_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -264,21 +282,17 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
             for (int c = 0; c < a.m_nc; ++c) {
               for (int q = 0; q < a.m_nq; ++q) {
                 const uint32_t a_lo = tap16 + (uint32_t)c * a.m_sc + (uint32_t)q * a.m_sq;
-                if (leader)
-                  h_mma(d_tmem, ((uint64_t)a.m_ahi << 32) | (uint64_t)a_lo, ((uint64_t)b_hi << 32) | (uint64_t)b_lo,
-                        idesc, accum);
+                h_mma_elect(d_tmem, ((uint64_t)a.m_ahi << 32) | (uint64_t)a_lo, ((uint64_t)b_hi << 32) | (uint64_t)b_lo,
+                            idesc, accum);
                 accum = 1;
                 b_lo += b_step;
               }
             }
           }
         }
-        if (leader) {
-          h_commit(halo_empty(s));
-          h_commit(tmem_full(acc));
-          h_stamp(it, 4);
-        }
-        __syncwarp();
+        h_commit_elect(halo_empty(s));
+        h_commit_elect(tmem_full(acc));
+        if (leader) h_stamp(it, 4);
       }
     }
   } else {
