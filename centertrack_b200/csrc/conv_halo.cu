@@ -16,7 +16,10 @@
 //
 // Warp roles (320 threads): warps 0-7 epilogue (warp w reads TMEM lanes 32(w%4)..; warps 0-3 take the even
 // 16-column chunks, 4-7 the odd ones -- the epilogue is instruction-latency bound, so two warps per SM
-// sub-partition), warp 8 TMA producer, warp 9 TMEM allocator + MMA issuer.
+// sub-partition), warp 8 TMA producer, warps 9 and 10 MMA issuers (warp 9 also owns the TMEM allocation).
+// TWO issuing warps because one thread sustains only one tcgen05.mma per ~100 cycles on B200 whatever N is
+// (tools/mma_rate.cu: 91-115 cycles for N <= 128; two warps on separate accumulators reach 64.6 = the N=128 floor):
+// warp 9 takes the even work items / accumulator 0, warp 10 the odd items / accumulator 1.
 #include "conv_common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
@@ -34,7 +37,7 @@ __device__ __forceinline__ void h_stamp(int it, int k) {
   unsigned long long* t = g_halo_trace;
   if (t != nullptr && blockIdx.x == 0 && it < 256) t[it * 8 + k] = (unsigned long long)clock64();
 }
-constexpr int H_THREADS = 320;           // 8 epilogue warps + TMA warp + MMA warp
+constexpr int H_THREADS = 352;           // 8 epilogue warps + TMA warp + 2 MMA warps
 constexpr int H_EPI_WARPS = 8;
 
 struct HaloArgs {
@@ -248,8 +251,8 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
         h_stamp(it, 1);
       }
     }
-  } else if (warp == 9) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 9 || warp == 10) {
+    // ===================== MMA issuers =====================
     // The whole warp runs this loop CONVERGENTLY and only the tcgen05.mma / commit statements are predicated on
     // the leader lane: the descriptors are then warp-uniform arithmetic on kernel parameters and loop counters,
     // which the compiler keeps in uniform registers.  (Issuing from a divergent `if (lane == 0)` region, or reading
@@ -261,8 +264,9 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
     const uint32_t b_step = ((uint32_t)a.n_tile * 32u) >> 4;          // descriptor start-address units (16 B)
     h_mbar_wait(w_full, 0);
     {
-      int it = 0;
-      for (int sp = sp0; sp < sp_total; sp += sp_stride, ++it) {
+      const int parity = warp - 9;                         // this warp's items: it % 2 == parity
+      int it = parity;
+      for (int sp = sp0 + parity * sp_stride; sp < sp_total; sp += 2 * sp_stride, it += 2) {
         const int s = it % S;
         const uint32_t ph = (uint32_t)(it / S) & 1u;
         const int acc = it & 1;
@@ -304,7 +308,7 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
     // Residual tiles are prefetched one work item ahead into registers (the load does not depend on the MMA):
     // issued right after the previous item consumed its copy, they land while this warp waits for the next
     // accumulator -- otherwise every item pays a full L2/HBM round trip inside the serial epilogue chain.
-    constexpr int PF = 4;                      // 16-column chunks per warp that can be prefetched (n_tile <= 128)
+    constexpr int PF = 2;                      // 16-column chunks per warp that can be prefetched (n_tile <= 64)
     uint4 rq[PF][2];
     const bool use_res = a.residual != nullptr && g.out_mode == CT_OUT_NHWC && !a.sum3;
     auto prefetch_residual = [&](int sp_n) {
