@@ -47,6 +47,7 @@ struct HaloArgs {
   const __nv_bfloat16* residual;
   void* out;
   int n_tile, n_tiles_n, nblk, planes, pw, ph, plane_bytes, box_bytes, halo_stages, tmem_cols;
+  int nacc;                             // TMEM accumulator stages (4 when 4*n_tile <= 512 columns, else 2)
   int tiles_x, tiles_y, tiles_total;    // spatial tiles per image / total work items (incl. n tiles)
   int pair_taps;                        // 1: C_in == 8, one MMA = taps (kx, kx+1)
   int swz;                              // 0: un-swizzled 8-channel planes; else row bytes (32/64/128): whole
@@ -185,18 +186,19 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
   const uint32_t sH = base + ((a.w_bytes + 1023u) & ~1023u);
   const uint32_t off_bar = ((a.w_bytes + 1023u) & ~1023u) + S * halo_bytes;
   const uint32_t bars = base + off_bar;
-  // barriers: w_full, halo_full[S], halo_empty[S], tmem_full[2], tmem_empty[2]
+  // barriers: w_full, halo_full[S], halo_empty[S], tmem_full[4], tmem_empty[4]
   const uint32_t w_full = bars;
   auto halo_full = [&](int s) { return bars + 8u * (1 + s); };
   auto halo_empty = [&](int s) { return bars + 8u * (1 + S + s); };
   auto tmem_full = [&](int s) { return bars + 8u * (1 + 2 * S + s); };
-  auto tmem_empty = [&](int s) { return bars + 8u * (3 + 2 * S + s); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + off_bar + 8 * (5 + 2 * S));
+  auto tmem_empty = [&](int s) { return bars + 8u * (5 + 2 * S + s); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + off_bar + 8 * (9 + 2 * S));
+  const int NACC = a.nacc;
 
   if (tid == 0) {
     h_mbar_init(w_full, 1);
     for (int s = 0; s < S; ++s) { h_mbar_init(halo_full(s), 1); h_mbar_init(halo_empty(s), 1); }
-    for (int s = 0; s < 2; ++s) { h_mbar_init(tmem_full(s), 1); h_mbar_init(tmem_empty(s), 32 * H_EPI_WARPS); }
+    for (int s = 0; s < 4; ++s) { h_mbar_init(tmem_full(s), 1); h_mbar_init(tmem_empty(s), 32 * H_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 9) {
@@ -269,8 +271,8 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
       for (int sp = sp0 + parity * sp_stride; sp < sp_total; sp += 2 * sp_stride, it += 2) {
         const int s = it % S;
         const uint32_t ph = (uint32_t)(it / S) & 1u;
-        const int acc = it & 1;
-        const uint32_t pa = (uint32_t)(it >> 1) & 1u;
+        const int acc = it % NACC;                 // warp `parity` owns accumulators parity, parity + 2
+        const uint32_t pa = (uint32_t)(it / NACC) & 1u;
         h_mbar_wait(halo_full(s), ph);
         if (leader) h_stamp(it, 2);
         h_mbar_wait(tmem_empty(acc), pa ^ 1u);
@@ -330,8 +332,8 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
     if (use_res && sp0 < sp_total) prefetch_residual(sp0);
     int it = 0;
     for (int sp = sp0; sp < sp_total; sp += sp_stride, ++it) {
-      const int acc = it & 1;
-      const uint32_t pa = (uint32_t)(it >> 1) & 1u;
+      const int acc = it % NACC;
+      const uint32_t pa = (uint32_t)(it / NACC) & 1u;
       const int b = sp / per_img, r = sp - b * per_img;
       const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
       const int oy = ty * HT_H + gy, ox = tx * HT_W + rx;
@@ -552,7 +554,8 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
   a.tiles_y = (g.OH + HT_H - 1) / HT_H;
   a.tiles_total = g.B * a.tiles_x * a.tiles_y;
   int cols = 32;
-  while (cols < 2 * n_tile) cols <<= 1;
+  a.nacc = 4 * n_tile <= 512 ? 4 : 2;
+  while (cols < a.nacc * n_tile) cols <<= 1;
   if (cols > 512) return fail(CT_ERR_INVALID, "conv_halo: n_tile too large for double-buffered TMEM%s", "");
   a.tmem_cols = cols;
   const size_t halo_bytes = (size_t)a.planes * a.plane_bytes;
