@@ -220,7 +220,7 @@ def main():
   # ---------------- roofline of the dominant kernel (conv_tc_kernel), measured live ----------------
   eng = runner.eng
   stream = torch.cuda.current_stream()
-  conv_ms, conv_flop, all_ms = 0.0, 0.0, 0.0
+  conv_ms, conv_flop, all_ms, halo_ms, halo_flop = 0.0, 0.0, 0.0, 0.0, 0.0
   reps = 3
   per_kind = {}
   for rep in range(reps):
@@ -236,19 +236,31 @@ def main():
       all_ms += dt
       key = 'dcn' if (kind == 'conv' and pl.a_mode == L.CT_A_DCN) else kind
       per_kind[key] = per_kind.get(key, 0.0) + dt / reps
+      fl = 2.0 * pl.B * pl.OH * pl.OW * pl.C_out * pl.KH * pl.KW * pl.C_in if kind == 'conv' else 0.0
+      if kind == 'conv' and pl.epilogue_sum3:
+        fl = 2.0 * pl.B * pl.OH * pl.OW * 16 * 49 * 7            # the three stems: 16 x (3+3+1) x 7x7 MACs/pixel
       if kind == 'conv' and pl.engine == L.CT_ENGINE_TCGEN05:
         conv_ms += dt
-        conv_flop += 2.0 * pl.B * pl.OH * pl.OW * pl.C_out * pl.KH * pl.KW * pl.C_in
+        conv_flop += fl
+      if kind == 'conv' and pl.engine == L.CT_ENGINE_TCGEN05_HALO:
+        halo_ms += dt
+        halo_flop += fl
   conv_ms /= reps
   conv_flop /= reps
+  halo_ms /= reps
+  halo_flop /= reps
   all_ms /= reps
   peak_tf, peak_hbm, peak_src = _peaks()
   achieved = conv_flop / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
-  roofline = {'kernel': 'conv_tc_kernel (all %d tcgen05 conv/DCN launches of one step)' %
-              sum(1 for k, p, n in eng.ops if k == 'conv'),
+  halo_tf = halo_flop / (halo_ms / 1000.0) / 1e12 if halo_ms > 0 else 0.0
+  roofline = {'kernel': 'conv_tc_kernel (all %d gather-engine tcgen05 conv/DCN launches of one step)' %
+              sum(1 for k, p, n in eng.ops if k == 'conv' and p.engine == L.CT_ENGINE_TCGEN05),
               'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
               'frac': achieved / peak_tf if peak_tf else None, 'traffic': None, 'peak_source': peak_src,
               'share_of_step': conv_ms / all_ms if all_ms else None,
+              'second_kernel': {'kernel': 'conv_halo_kernel (%d launches)' % sum(1 for k, p, n in eng.ops if k == 'conv' and p.engine == L.CT_ENGINE_TCGEN05_HALO),
+                                'achieved': halo_tf, 'frac': halo_tf / peak_tf if peak_tf else None,
+                                'share_of_step': halo_ms / all_ms if all_ms else None},
               'eager_ms_by_kind': {k: round(v, 3) for k, v in per_kind.items()},
               'whole_step_tflops': GFLOP_PER_FRAME * B / ms_per_step}
 

@@ -13,7 +13,9 @@ from centertrack_b200 import _lib as L       # noqa
 from gpu_helpers import run_conv             # noqa
 
 lib = L.lib()
-cases = [('heads.0 64->1024 nt128 128x128', 16, 64, 1024, 128, 128, 3, False, 128),
+cases = [('stem 7x7 8->48 sum3 512x512', 16, 8, 48, 512, 512, 7, False, 48),
+         ('level0 16->16 512x512', 16, 16, 16, 512, 512, 3, False, 16),
+         ('heads.0 64->1024 nt128 128x128', 16, 64, 1024, 128, 128, 3, False, 128),
          ('level2 64->64 +res 128x128', 16, 64, 64, 128, 128, 3, True, 64),
          ('level3 128->128 +res nt32 64x64', 16, 128, 128, 64, 64, 3, True, 32),
          ('offset 64->27 nt32 128x128', 16, 64, 32, 128, 128, 3, False, 32),
@@ -30,9 +32,11 @@ for (name, B, Cin, Cout, H, W, k, res, nt) in cases:
   b = torch.zeros(Cout)
   r = torch.randn(B, Cout, H, W, generator=g).cuda() if res else None
   tr = torch.zeros(256 * 8, dtype=torch.int64, device='cuda')
-  run_conv(L.CT_ENGINE_TCGEN05_HALO, L.CT_BF16, x.cuda(), w, b, 1, True, r, n_tile=nt)     # warm
+  kw = dict(n_tile=nt, sum3=7) if Cin == 8 else dict(n_tile=nt)
+  relu = Cin != 8
+  run_conv(L.CT_ENGINE_TCGEN05_HALO, L.CT_BF16, x.cuda(), w, b, 1, relu, r, **kw)     # warm
   L.check(lib.ct_debug_trace(C.c_void_p(tr.data_ptr())))
-  run_conv(L.CT_ENGINE_TCGEN05_HALO, L.CT_BF16, x.cuda(), w, b, 1, True, r, n_tile=nt)
+  run_conv(L.CT_ENGINE_TCGEN05_HALO, L.CT_BF16, x.cuda(), w, b, 1, relu, r, **kw)
   torch.cuda.synchronize()
   L.check(lib.ct_debug_trace(None))
   t = tr.cpu().numpy().reshape(256, 8).astype(np.int64)
@@ -40,11 +44,11 @@ for (name, B, Cin, Cout, H, W, k, res, nt) in cases:
   t0 = t[0, 0]
   print('==== %s : %d items in CTA 0' % (name, n))
   print('  it   prod_acq  tma_iss | mma_halo mma_acc  mma_done | epi_start epi_done   (cycles since start; item period)')
-  for i in list(range(min(n, 6))) + list(range(max(6, n - 3), n)):
+  for i in list(range(min(n, 8))) + list(range(max(8, n - 2), n)):
     row = t[i] - t0
     per = (t[i, 4] - t[i - 1, 4]) if i > 0 else 0
     print('  %3d %9d %8d | %8d %8d %8d | %8d %8d   period %d' % (i, row[0], row[1], row[2], row[3], row[4], row[5], row[6], per))
-  nblk = (k * k * (Cin // 16))
+  nblk = (k * k * (Cin // 16)) if Cin != 8 else k * ((k + 1) // 2)
   if n > 4:
     print('  issue phase per MMA: %.0f cycles (nblk %d); period per MMA %.0f' % (np.mean(t[2:n, 4] - t[2:n, 3]) / nblk, nblk, np.mean(np.diff(t[1:n, 4])) / nblk))
   if n > 4:
