@@ -264,6 +264,17 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
     const uint32_t b_hi = (uint32_t)(h_sdesc(0, (uint32_t)a.n_tile * 16u, 128u) >> 32);
     const uint32_t b_lo0 = (uint32_t)h_sdesc(sW, (uint32_t)a.n_tile * 16u, 128u);
     const uint32_t b_step = ((uint32_t)a.n_tile * 32u) >> 4;          // descriptor start-address units (16 B)
+    // per-warp table of A-descriptor low words for halo stage 0 (walk: ky, kx|pair, chunk, K-step)
+    uint32_t* a_tab = reinterpret_cast<uint32_t*>(sm + off_bar + 128 + 1024) + (warp - 9) * 160;
+    for (int blk = lane; blk < a.nblk; blk += 32) {
+      int r = blk;
+      const int q = r % a.m_nq; r /= a.m_nq;
+      const int c = r % a.m_nc; r /= a.m_nc;
+      const int kx = r % a.m_nkx, ky = r / a.m_nkx;
+      a_tab[blk] = a.m_alo + (sH >> 4) + (uint32_t)ky * a.m_sky + (uint32_t)kx * a.m_skx + (uint32_t)c * a.m_sc +
+                   (uint32_t)q * a.m_sq;
+    }
+    __syncwarp();
     h_mbar_wait(w_full, 0);
     {
       const int parity = warp - 9;                         // this warp's items: it % 2 == parity
@@ -278,22 +289,21 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
         h_mbar_wait(tmem_empty(acc), pa ^ 1u);
         if (leader) h_stamp(it, 3);
         h_fence_after();
-        const uint32_t base16 = a.m_alo + ((sH + (uint32_t)s * halo_bytes) >> 4);   // start address stays < 2^14
+        const uint32_t stage16 = ((uint32_t)s * halo_bytes) >> 4;      // start address field stays < 2^14
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.n_tile);
         uint32_t b_lo = b_lo0;
         uint32_t accum = 0;
-        for (int ky = 0; ky < a.m_nky; ++ky) {
-          for (int kx = 0; kx < a.m_nkx; ++kx) {
-            const uint32_t tap16 = base16 + (uint32_t)ky * a.m_sky + (uint32_t)kx * a.m_skx;
-            for (int c = 0; c < a.m_nc; ++c) {
-              for (int q = 0; q < a.m_nq; ++q) {
-                const uint32_t a_lo = tap16 + (uint32_t)c * a.m_sc + (uint32_t)q * a.m_sq;
-                h_mma_elect(d_tmem, ((uint64_t)a.m_ahi << 32) | (uint64_t)a_lo, ((uint64_t)b_hi << 32) | (uint64_t)b_lo,
-                            idesc, accum);
-                accum = 1;
-                b_lo += b_step;
-              }
-            }
+        // A-descriptor low words of this item's MMAs: one shared-memory load per 32 MMAs (lane j holds block j),
+        // then a register shuffle + add per MMA -- nothing else varies (B advances by a uniform step)
+        for (int blk0 = 0; blk0 < a.nblk; blk0 += 32) {
+          const uint32_t mine = a_tab[min(blk0 + lane, a.nblk - 1)];
+          const int cnt = min(32, a.nblk - blk0);
+          for (int j = 0; j < cnt; ++j) {
+            const uint32_t a_lo = __shfl_sync(0xffffffffu, mine, j) + stage16;
+            h_mma_elect(d_tmem, ((uint64_t)a.m_ahi << 32) | (uint64_t)a_lo, ((uint64_t)b_hi << 32) | (uint64_t)b_lo,
+                        idesc, accum);
+            accum = 1;
+            b_lo += b_step;
           }
         }
         h_commit_elect(halo_empty(s));
@@ -516,6 +526,7 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
   a.n_tiles_n = (g.C_out + n_tile - 1) / n_tile;
   a.pair_taps = g.C_in == 8;
   a.nblk = halo_blocks(g.C_in, g.KH, g.KW);
+  if (a.nblk > 160) return fail(CT_ERR_UNSUPPORTED, "conv_halo: more than 160 K=16 blocks per tile%s (%ld)", "", (long)a.nblk);
   // operand staging mode: whole-pixel swizzled rows when C_in*2 is a swizzle width (one 32/64/128-byte TMA
   // request per halo pixel); C_in == 8 keeps the 16-byte un-swizzled rows but merges (x, c) in the tensor map
   // when the tensor is dense (ld_in == 8) so that one request covers a whole halo row.
@@ -560,7 +571,7 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
   a.tmem_cols = cols;
   const size_t halo_bytes = (size_t)a.planes * a.plane_bytes;
   int stages = 3;
-  auto smem_for = [&](int s) { return (size_t)((a.w_bytes + 1023) & ~1023u) + s * halo_bytes + 128 + 1024 + 1024; };
+  auto smem_for = [&](int s) { return (size_t)((a.w_bytes + 1023) & ~1023u) + s * halo_bytes + 128 + 1024 + 2 * 160 * 4 + 1024; };
   while (stages > 2 && smem_for(stages) > 220 * 1024) --stages;
   if (smem_for(stages) > 227 * 1024)
     return fail(CT_ERR_UNSUPPORTED, "conv_halo: weights + halo do not fit in shared memory%s (%ld bytes)", "",
