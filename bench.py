@@ -120,7 +120,7 @@ def main():
   ap.add_argument('--gpus', type=int, default=1)
   ap.add_argument('--steps', type=int, default=30)
   ap.add_argument('--warmup', type=int, default=5)
-  ap.add_argument('--batch', type=int, default=16, help='frames (independent streams) per GPU per step')
+  ap.add_argument('--batch', type=int, default=32, help='frames (independent streams) per GPU per step')
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
   ap.add_argument('--no-cpu-baseline', action='store_true')

@@ -95,30 +95,8 @@ __global__ void pack_stem_kernel(const float* __restrict__ img, const float* __r
 }
 
 // ------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void maxpool2_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, int W, int C,
-                                int ld_in, int ld_out) {
-  const int OH = H / 2, OW = W / 2;
-  const size_t total = (size_t)B * OH * OW * C;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const int c = i % C;
-    size_t p = i / C;
-    const int ox = p % OW; p /= OW;
-    const int oy = p % OH;
-    const int b = p / OH;
-    const T* s = x + (((size_t)b * H + 2 * oy) * W + 2 * ox) * ld_in + c;
-    const float v = fmaxf(fmaxf(Elem<T>::ld(s), Elem<T>::ld(s + ld_in)),
-                          fmaxf(Elem<T>::ld(s + (size_t)W * ld_in), Elem<T>::ld(s + (size_t)(W + 1) * ld_in)));
-    Elem<T>::st(out + (((size_t)b * OH + oy) * OW + ox) * ld_out + c, v);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// depthwise ConvTranspose2d(k=2f, stride f, pad f/2, no bias) + skip  (dla.py:529-531,543-545)
-// One thread = one output pixel x 16 bytes of channels (8 bf16 / 4 fp32): every access is a full
-// 16-byte vector, consecutive threads walk consecutive channel groups then pixels (coalesced).
-// w is channel-last: fp32 [2f][2f][C].
+// Tree.downsample: 2x2 max-pool, 16-byte vectors (8 bf16 / 4 fp32 channels per thread), output may be a channel
+// slice of a concat buffer (ld_out)
 // ------------------------------------------------------------------------------------------
 template <typename T> struct VecIO;
 template <> struct VecIO<float> {
@@ -148,6 +126,35 @@ template <> struct VecIO<__nv_bfloat16> {
   }
 };
 
+template <typename T>
+__global__ void maxpool2_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, int W, int C,
+                                int ld_in, int ld_out) {
+  constexpr int V = VecIO<T>::N;
+  const int OH = H / 2, OW = W / 2, CV = C / V;
+  const size_t total = (size_t)B * OH * OW * CV;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % CV) * V;
+    size_t p = i / CV;
+    const int ox = p % OW; p /= OW;
+    const int oy = p % OH;
+    const int b = p / OH;
+    const T* s = x + (((size_t)b * H + 2 * oy) * W + 2 * ox) * ld_in + c;
+    float v0[V], v1[V], v2[V], v3[V];
+    VecIO<T>::ld(s, v0); VecIO<T>::ld(s + ld_in, v1);
+    VecIO<T>::ld(s + (size_t)W * ld_in, v2); VecIO<T>::ld(s + (size_t)(W + 1) * ld_in, v3);
+#pragma unroll
+    for (int q = 0; q < V; ++q) v0[q] = fmaxf(fmaxf(v0[q], v1[q]), fmaxf(v2[q], v3[q]));
+    VecIO<T>::st(out + (((size_t)b * OH + oy) * OW + ox) * ld_out + c, v0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// depthwise ConvTranspose2d(k=2f, stride f, pad f/2, no bias) + skip  (dla.py:529-531,543-545)
+// One thread = one output pixel x 16 bytes of channels (8 bf16 / 4 fp32): every access is a full
+// 16-byte vector, consecutive threads walk consecutive channel groups then pixels (coalesced).
+// w is channel-last: fp32 [2f][2f][C].
+// ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void upsample_add_kernel(const T* __restrict__ x, const T* __restrict__ skip,
                                     const float* __restrict__ w, T* __restrict__ out, int B, int H, int W,
@@ -261,7 +268,9 @@ extern "C" int ct_maxpool2(const void* x, void* out, int32_t dtype, int32_t B, i
                            int32_t C, int32_t ld_in, int32_t ld_out, void* stream) {
   CT_REQUIRE(x && out, "null pointer");
   CT_REQUIRE(H % 2 == 0 && W % 2 == 0, "odd spatial size");
-  const size_t total = (size_t)B * (H / 2) * (W / 2) * C;
+  const int vecw = dtype == CT_F32 ? 4 : 8;
+  CT_REQUIRE(C % vecw == 0 && ld_in % vecw == 0 && ld_out % vecw == 0, "channels / strides must be multiples of 16 bytes");
+  const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / vecw);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == CT_F32)
     maxpool2_kernel<float><<<ew_blocks(total), 256, 0, st>>>((const float*)x, (float*)out, B, H, W, C, ld_in, ld_out);
