@@ -57,7 +57,7 @@ class DecodeDesc(C.Structure):
 EXPORTS = ['ct_packed_weight_bytes', 'ct_pack_weights', 'ct_conv_forward', 'ct_stem_forward',
            'ct_pack_stem_input', 'ct_maxpool2', 'ct_upsample_add', 'ct_decode_workspace_bytes', 'ct_decode',
            'ct_render_pre_hm', 'ct_last_error', 'ct_abi_version', 'ct_launch_count',
-           'ct_reset_launch_count', 'ct_debug_trace']
+           'ct_reset_launch_count', 'ct_debug_trace', 'ct_debug_watch']
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
@@ -109,6 +109,7 @@ def lib():
   L.ct_launch_count.restype = C.c_int64
   L.ct_reset_launch_count.restype = None
   L.ct_debug_trace.argtypes = [C.c_void_p]
+  L.ct_debug_watch.argtypes = [C.c_void_p]
   if L.ct_abi_version() != 1:
     raise RuntimeError('libctb200 ABI mismatch')
   _lib = L

@@ -74,6 +74,7 @@ class DLA34Engine(object):
     self.named = {}        # name -> TV (for per-stage parity tests)
     self.head_descs = {}   # head -> final ConvDesc (to toggle the fused activation)
     self.n_sm = 148
+    self.debug_sync = bool(int(__import__('os').environ.get('CTB_DEBUG_SYNC', '0')))
     self.use_halo = use_halo and precision == 'bf16'
     self._build()
     self.graph = None
@@ -412,6 +413,11 @@ class DLA34Engine(object):
                                self.ct_dtype, self.B, x.H, x.W, x.C, f, x.ld, skip.ld, o.ld, st)
     if rc != 0:
       L.check(rc, '%s (%s)' % (kind, name))
+    if self.debug_sync:                  # CTB_DEBUG_SYNC=1: attribute an asynchronous kernel fault to its layer
+      try:
+        torch.cuda.synchronize()
+      except Exception as e:
+        raise RuntimeError('kernel fault in op %s (%s): %s' % (kind, name, e))
 
   def _run_ops(self, img_ptr, pre_ptr, hm_ptr):
     st = L.stream_ptr()
