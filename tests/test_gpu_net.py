@@ -252,16 +252,24 @@ def test_detector_run_three_frames_matches_oracle_pipeline():
     pre_img_t = images
     got = ret['results']
     assert len(got) > 0
-    # match by tracking id order; allow a few near-threshold detections to differ
+    # the two lists are matched by box (the random-weight network produces many near-equal scores, so list
+    # order and greedy association are not stable under 1e-6 differences); a few near-threshold detections may differ
     assert abs(len(got) - len(ref)) <= max(2, len(ref) // 20)
-    n = min(len(got), len(ref))
-    ids_g = [r['tracking_id'] for r in got[:n]]
-    ids_r = [r['tracking_id'] for r in ref[:n]]
-    agree = np.mean([a == b for a, b in zip(ids_g, ids_r)])
-    assert agree >= 0.9, (fi, agree)
-    for a, b in zip(got[:n], ref[:n]):
-      if a['tracking_id'] == b['tracking_id'] and abs(a['score'] - b['score']) < 1e-4:
-        assert np.abs(np.asarray(a['bbox']) - np.asarray(b['bbox'])).max() < 0.05
+    gb = np.asarray([r['bbox'] for r in got], np.float32)
+    matched, same_id, miss = 0, 0, []
+    for b in ref:
+      d = np.abs(gb - np.asarray(b['bbox'], np.float32)[None]).max(1)
+      # boxes are in image pixels (tens of px wide): 1e-3 x |wh| head tolerance -> a fraction of a pixel; several
+      # classes can peak at the same cell and share one box, so the class takes part in the match
+      cand = [j for j in np.nonzero(d < 0.5)[0]
+              if got[j]['class'] == b['class'] and abs(got[j]['score'] - b['score']) < 1e-3]
+      if cand:
+        matched += 1
+        same_id += got[cand[0]]['tracking_id'] == b['tracking_id']
+      else:
+        miss.append((float(d.min()), b['class'], float(b['score'])))
+    assert matched >= 0.9 * len(ref), (fi, matched, len(ref), miss)
+    assert same_id >= 0.9 * matched, (fi, same_id, matched)
 
 
 @pytest.mark.parametrize('cfg,hw', [('mot', (544, 960)), ('nuscenes_ddd', (448, 800)), ('coco_pose', (512, 512))])
