@@ -127,24 +127,40 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
 // weights already multiplied by the modulation mask and zeroed for corners / samples outside the image.
 struct __align__(16) DcnEntry { int off, dxo, dyo, pad; float w00, w01, w10, w11; };   // 32 bytes
 
-__device__ __forceinline__ void blend8(float (&acc)[8], uint4 v, float w) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float2 f = __bfloat1622float2(h[q]);
-    acc[2 * q] = fmaf(w, f.x, acc[2 * q]);
-    acc[2 * q + 1] = fmaf(w, f.y, acc[2 * q + 1]);
-  }
+// bf16x2 word -> two fp32 lanes of one 64-bit register (lo = x << 16, hi = x & 0xffff0000: one ALU op each), then
+// packed fp32 math (FMUL2 / FFMA2): 8 channels x 1 corner = 8 unpack + 4 packed FMAs.
+__device__ __forceinline__ unsigned long long bf2_to_f2(uint32_t x) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(x << 16), "r"(x & 0xffff0000u));
+  return r;
 }
-
-__device__ __forceinline__ void scale8(float (&acc)[8], uint4 v, float w) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+__device__ __forceinline__ unsigned long long dup_f2(float w) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "r"(__float_as_uint(w)));
+  return r;
+}
+__device__ __forceinline__ void scale8(unsigned long long (&acc)[4], uint4 v, float w) {
+  const unsigned long long ww = dup_f2(w);
+  const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(acc[q]) : "l"(bf2_to_f2(x[q])), "l"(ww));
+}
+__device__ __forceinline__ void blend8(unsigned long long (&acc)[4], uint4 v, float w) {
+  const unsigned long long ww = dup_f2(w);
+  const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[q]) : "l"(bf2_to_f2(x[q])), "l"(ww));
+}
+__device__ __forceinline__ uint4 pack8(const unsigned long long (&acc)[4]) {
+  uint32_t o[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const float2 f = __bfloat1622float2(h[q]);
-    acc[2 * q] = w * f.x;
-    acc[2 * q + 1] = w * f.y;
+    uint32_t lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(acc[q]));
+    const __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(lo), __uint_as_float(hi));
+    o[q] = *reinterpret_cast<const uint32_t*>(&h);
   }
+  return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 2)
@@ -256,6 +272,61 @@ conv_tc_kernel(const TcArgs a) {
     const int ntaps = g.KH * g.KW;
     const __nv_bfloat16* wt = a.w + (size_t)nt * a.k_slices * a.n_tile * TC_BK;
 
+    if (a.a_mode == CT_A_DCN) {
+      // Software-pipelined by half slices (2 of the thread's 4 rows): the 8 corner loads of the next half are in
+      // flight while the current half is blended (the gather is latency-bound -- memory-level parallelism first --
+      // and the blend is issue-bound: packed FFMA2, one-op bf16 unpack).  A slice whose tap index runs past the
+      // kernel (K padding) samples tap 0 with its result zeroed.
+      uint4 va[2][4], vb[2][4];
+      auto load_half = [&](int tap, int c, int half, uint4 (&v)[2][4]) {
+        const DcnEntry* tab = dcn_tab + (tap < ntaps ? tap : 0) * TC_BM + r0 + 64 * half;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int4 o = *reinterpret_cast<const int4*>(&tab[32 * j]);     // off, dxo, dyo
+          const __nv_bfloat16* p00 = a.x + (o.x + c);
+          v[j][0] = ldg_nc16(p00);
+          v[j][1] = ldg_nc16(p00 + o.y);
+          v[j][2] = ldg_nc16(p00 + o.z);
+          v[j][3] = ldg_nc16(p00 + o.z + o.y);
+        }
+      };
+      auto blend_half = [&](int tap, int stage, int half, const uint4 (&v)[2][4]) {
+        const bool live = tap < ntaps;
+        const DcnEntry* tab = dcn_tab + (live ? tap : 0) * TC_BM + r0 + 64 * half;
+        const uint32_t dst = sA + stage * A_STAGE_BYTES + (uint32_t)(r0 + 64 * half) * 128u + swz;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float4 w = *reinterpret_cast<const float4*>(&tab[32 * j].w00);
+          unsigned long long acc[4];
+          scale8(acc, v[j][0], w.x);
+          blend8(acc, v[j][1], w.y);
+          blend8(acc, v[j][2], w.z);
+          blend8(acc, v[j][3], w.w);
+          sts16(dst + j * 4096u, live ? pack8(acc) : make_uint4(0, 0, 0, 0));
+        }
+      };
+      // (tap, channel group) of this thread's 8-channel column in slice s, advanced incrementally (no division)
+      int tap = q / cin8, cq = q - tap * cin8;
+      load_half(tap, cq << 3, 0, va);
+      for (int s = 0; s < a.k_slices; ++s) {
+        const int stage = s % S;
+        const uint32_t ph = (uint32_t)(s / S) & 1u;
+        load_half(tap, cq << 3, 1, vb);
+        mbar_wait(empty_bar(stage), ph ^ 1u);
+        if (tid == 0) {
+          mbar_expect_tx(full_bar(stage), b_stage_bytes);
+          bulk_g2s(sB + stage * b_stage_bytes, wt + (size_t)s * a.n_tile * TC_BK, b_stage_bytes, full_bar(stage));
+        }
+        blend_half(tap, stage, 0, va);
+        int ntap = tap, ncq = cq + 8;
+        while (ncq >= cin8) { ncq -= cin8; ++ntap; }
+        if (s + 1 < a.k_slices) load_half(ntap, ncq << 3, 0, va);
+        blend_half(tap, stage, 1, vb);
+        tap = ntap; cq = ncq;
+        fence_proxy_async();
+        mbar_arrive(full_bar(stage));
+      }
+    } else
     for (int s = 0; s < a.k_slices; ++s) {
       const int stage = s % S;
       const uint32_t ph = (uint32_t)(s / S) & 1u;
@@ -283,34 +354,6 @@ conv_tc_kernel(const TcArgs a) {
         }
 #pragma unroll
         for (int i = 0; i < TC_NROW; ++i) sts16(dst + i * 4096u, v[i]);
-      } else {
-        // 4 rows x 4 bilinear corners = 16 independent, unpredicated 16-byte loads in flight per thread before
-        // any blend (latency-bound gather: memory-level parallelism first), then ~20 instructions per corner.
-        const DcnEntry* tab = dcn_tab + tap * TC_BM + r0;
-        DcnEntry e[TC_NROW];
-        uint4 v[TC_NROW][4];
-#pragma unroll
-        for (int j = 0; j < TC_NROW; ++j) {
-          e[j] = tab[32 * j];
-          const __nv_bfloat16* p00 = a.x + (e[j].off + c);
-          v[j][0] = ldg_nc16(p00);
-          v[j][1] = ldg_nc16(p00 + e[j].dxo);
-          v[j][2] = ldg_nc16(p00 + e[j].dyo);
-          v[j][3] = ldg_nc16(p00 + e[j].dyo + e[j].dxo);
-        }
-#pragma unroll
-        for (int j = 0; j < TC_NROW; ++j) {
-          float acc[8];
-          scale8(acc, v[j][0], e[j].w00);
-          blend8(acc, v[j][1], e[j].w01);
-          blend8(acc, v[j][2], e[j].w10);
-          blend8(acc, v[j][3], e[j].w11);
-          uint4 o;
-          __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) oh[q] = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
-          sts16(dst + j * 4096u, o);
-        }
       }
       fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       mbar_arrive(full_bar(stage));
