@@ -22,7 +22,10 @@ extern "C" const char* ct_last_error(void) { return g_err; }
 extern "C" int ct_abi_version(void) { return CTB200_ABI_VERSION; }
 extern "C" int64_t ct_launch_count(void) { return g_launches; }
 extern "C" void ct_reset_launch_count(void) { g_launches = 0; }
-extern "C" int ct_debug_trace(void* device_buf) { return halo_set_trace(device_buf); }
+extern "C" int ct_debug_trace(void* device_buf) {
+  const int r = halo_set_trace(device_buf);
+  return r != CT_OK ? r : tc_set_trace(device_buf);
+}
 extern "C" int ct_debug_watch(void* mapped_host_buf) { return halo_set_watch(mapped_host_buf); }
 
 static inline int tc_k_slices(int C_in, int KH, int KW) { return (KH * KW * C_in + 63) / 64; }

@@ -68,6 +68,7 @@ int conv_forward_tc(const ct_conv_desc* d, cudaStream_t st);
 int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st);
 int halo_blocks(int C_in, int KH, int KW);
 int halo_set_trace(void* buf);
+int tc_set_trace(void* buf);
 int halo_set_watch(void* mapped_host_buf);
 
 }  // namespace ctb

@@ -19,6 +19,7 @@
 // (two per SM sub-partition) because the gather is latency-bound: more warps = more loads in flight.
 // Two CTAs are co-resident per SM so one CTA's epilogue overlaps another's main loop.
 #include "conv_common.cuh"
+#include <stdlib.h>
 
 namespace ctb {
 
@@ -38,7 +39,28 @@ struct TcArgs {
   const float* om;
   void* out;
   int n_tile, k_slices, stages, tmem_cols, a_mode;
+  int tiles_x, tiles_y;         // > 0: an M tile is an 8 (y) x 16 (x) pixel patch of one image (L1 reuse of the
+                                // 3x3 / bilinear footprints); 0: 128 consecutive pixels in b,y,x order
 };
+
+// output pixel (linear b,y,x index) of GEMM row r of M tile mt; g.P_out when the row is padding
+__device__ __forceinline__ int tc_pixel(const TcArgs& a, int mt, int r) {
+  const ConvGeom& g = a.g;
+  if (a.tiles_x == 0) { const int p = mt * TC_BM + r; return p < g.P_out ? p : g.P_out; }
+  const int tpi = a.tiles_x * a.tiles_y;
+  const int b = mt / tpi, t = mt - b * tpi;
+  const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+  const int oy = ty * 8 + (r >> 4), ox = tx * 16 + (r & 15);
+  return (oy < g.OH && ox < g.OW) ? (b * g.OH + oy) * g.OW + ox : g.P_out;
+}
+
+// Optional timeline of the middle CTA (ct_debug_trace): clock64() stamps -- 0 start, 1 rows set up, 2 DCN table built,
+// 8+s producer warp 0 finished slice s, 4 MMA warp committed, 5 epilogue saw the accumulator, 6 epilogue done.
+__device__ unsigned long long* g_tc_trace = nullptr;
+__device__ __forceinline__ void tc_stamp(int k) {
+  unsigned long long* t = g_tc_trace;
+  if (t != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && k < 256) t[k] = (unsigned long long)clock64();
+}
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -185,9 +207,10 @@ conv_tc_kernel(const TcArgs a) {
   auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
   const uint32_t tmem_full_bar = bars + 8u * (2 * S);
 
-  const int m0 = blockIdx.x * TC_BM;
+  const int mt = blockIdx.x;
   const int nt = blockIdx.y;
   const int n0 = nt * a.n_tile;
+  if (tid == 0) tc_stamp(0);
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), TC_PRODUCERS); mbar_init(empty_bar(s), 1); }
@@ -205,6 +228,7 @@ conv_tc_kernel(const TcArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) tc_stamp(7);
 
   if (warp < 8) {
     // =========================== A producers ===========================
@@ -215,7 +239,7 @@ conv_tc_kernel(const TcArgs a) {
     int row_off[TC_NROW], row_iy[TC_NROW], row_ix[TC_NROW];   // element offset / coords of the window's top-left input pixel
 #pragma unroll
     for (int i = 0; i < TC_NROW; ++i) {
-      const int p = m0 + r0 + 32 * i;
+      const int p = tc_pixel(a, mt, r0 + 32 * i);
       if (p < g.P_out) {
         const int b = p / HWo, r = p - b * HWo;
         const int oy = r / g.OW, ox = r - oy * g.OW;
@@ -226,10 +250,11 @@ conv_tc_kernel(const TcArgs a) {
         row_off[i] = 0; row_iy[i] = -100000; row_ix[i] = -100000;
       }
     }
+    if (tid == 0) tc_stamp(1);
     if (a.a_mode == CT_A_DCN) {
       // per (tap,row) sampling records, computed once per CTA (row = tid, threads 0..127)
-      const int p = m0 + tid;
-      const bool ok = p < g.P_out && tid < TC_BM;
+      const int p = tid < TC_BM ? tc_pixel(a, mt, tid) : g.P_out;
+      const bool ok = p < g.P_out;
       if (tid < TC_BM) {
         int oy = 0, ox = 0, img = 0;
         float om[28];
@@ -267,6 +292,7 @@ conv_tc_kernel(const TcArgs a) {
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tid == 0) tc_stamp(2);
     }
     const int cin8 = g.C_in >> 3;
     const int ntaps = g.KH * g.KW;
@@ -325,46 +351,62 @@ conv_tc_kernel(const TcArgs a) {
         tap = ntap; cq = ncq;
         fence_proxy_async();
         mbar_arrive(full_bar(stage));
+        if (tid == 0) tc_stamp(8 + s);
       }
-    } else
-    for (int s = 0; s < a.k_slices; ++s) {
-      const int stage = s % S;
-      const uint32_t ph = (uint32_t)(s / S) & 1u;
-      mbar_wait(empty_bar(stage), ph ^ 1u);
-      if (tid == 0) {
-        mbar_expect_tx(full_bar(stage), b_stage_bytes);
-        bulk_g2s(sB + stage * b_stage_bytes, wt + (size_t)s * a.n_tile * TC_BK, b_stage_bytes, full_bar(stage));
-      }
-      const int kc = s * 8 + q;
-      const int tap = kc / cin8;
-      const int c = (kc - tap * cin8) << 3;
-      const uint32_t dst = sA + stage * A_STAGE_BYTES + (uint32_t)r0 * 128u + swz;
-      if (tap >= ntaps) {
+    } else {
+      // Plain convolution gather, register-prefetched three K slices ahead (12 independent 16-byte loads in flight
+      // per thread): one slice's loads alone leave the loop bound by the L2 round trip (~1700 cycles per slice
+      // measured with tools/tc_trace.py).  (tap, channel group) advance incrementally with the load order.
+      int ltap = q / cin8, lcq = q - ltap * cin8;
+      auto load_slice = [&](bool in_range, uint4 (&v)[TC_NROW]) {
 #pragma unroll
-        for (int i = 0; i < TC_NROW; ++i) sts16(dst + i * 4096u, make_uint4(0, 0, 0, 0));
-      } else if (a.a_mode == CT_A_CONV) {
-        const int ky = tap / g.KW, kx = tap - ky * g.KW;
-        const int tap_off = (ky * g.W + kx) * g.ld_in + c;      // same for every row of the slice
-        uint4 v[TC_NROW];
+        for (int i = 0; i < TC_NROW; ++i) v[i] = make_uint4(0, 0, 0, 0);
+        if (in_range && ltap < ntaps) {
+          const int ky = ltap / g.KW, kx = ltap - ky * g.KW;
+          const int tap_off = (ky * g.W + kx) * g.ld_in + (lcq << 3);      // same for every row of the slice
 #pragma unroll
-        for (int i = 0; i < TC_NROW; ++i) {
-          v[i] = make_uint4(0, 0, 0, 0);
-          if ((unsigned)(row_iy[i] + ky) < (unsigned)g.H && (unsigned)(row_ix[i] + kx) < (unsigned)g.W)
-            v[i] = ldg_nc16(a.x + (row_off[i] + tap_off));
+          for (int i = 0; i < TC_NROW; ++i)
+            if ((unsigned)(row_iy[i] + ky) < (unsigned)g.H && (unsigned)(row_ix[i] + kx) < (unsigned)g.W)
+              v[i] = ldg_nc16(a.x + (row_off[i] + tap_off));
         }
+        lcq += 8;
+        while (lcq >= cin8) { lcq -= cin8; ++ltap; }
+      };
+      auto store_slice = [&](int s, const uint4 (&v)[TC_NROW]) {
+        const int stage = s % S;
+        const uint32_t ph = (uint32_t)(s / S) & 1u;
+        mbar_wait(empty_bar(stage), ph ^ 1u);
+        if (tid == 0) {
+          mbar_expect_tx(full_bar(stage), b_stage_bytes);
+          bulk_g2s(sB + stage * b_stage_bytes, wt + (size_t)s * a.n_tile * TC_BK, b_stage_bytes, full_bar(stage));
+        }
+        const uint32_t dst = sA + stage * A_STAGE_BYTES + (uint32_t)r0 * 128u + swz;
 #pragma unroll
         for (int i = 0; i < TC_NROW; ++i) sts16(dst + i * 4096u, v[i]);
+        fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        mbar_arrive(full_bar(stage));
+        if (tid == 0) tc_stamp(8 + s);
+      };
+      const int KS = a.k_slices;
+      uint4 v0[TC_NROW], v1[TC_NROW], v2[TC_NROW];
+      load_slice(0 < KS, v0);
+      load_slice(1 < KS, v1);
+      load_slice(2 < KS, v2);
+      for (int s = 0; s < KS; s += 3) {
+        store_slice(s, v0);
+        load_slice(s + 3 < KS, v0);
+        if (s + 1 < KS) { store_slice(s + 1, v1); load_slice(s + 4 < KS, v1); }
+        if (s + 2 < KS) { store_slice(s + 2, v2); load_slice(s + 5 < KS, v2); }
       }
-      fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-      mbar_arrive(full_bar(stage));
     }
 
     // =========================== epilogue ===========================
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (tid == 0) tc_stamp(5);
     const int wq = warp & 3, chalf = warp >> 2;      // TMEM lane quarter, column-chunk parity
     const int row = wq * 32 + lane;
-    const int p = m0 + row;
+    const int p = tc_pixel(a, mt, row);
     const bool p_ok = p < g.P_out;
     const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16);
     for (int col = chalf * 16; col < a.n_tile; col += 32) {
@@ -449,15 +491,22 @@ conv_tc_kernel(const TcArgs a) {
       tc_commit(empty_bar(stage));     // frees this smem stage when the MMAs above have read it
     }
     tc_commit(tmem_full_bar);           // accumulator complete -> epilogue
+    tc_stamp(4);
   }
 
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) tc_stamp(6);
   if (warp == 8) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols)
                  : "memory");
   }
+}
+
+int tc_set_trace(void* buf) {
+  unsigned long long* p = (unsigned long long*)buf;
+  return cudaMemcpyToSymbol(g_tc_trace, &p, sizeof(p)) == cudaSuccess ? CT_OK : CT_ERR_CUDA;
 }
 
 int conv_forward_tc(const ct_conv_desc* d, cudaStream_t st) {
@@ -510,7 +559,17 @@ int conv_forward_tc(const ct_conv_desc* d, cudaStream_t st) {
     smem_set = 200 * 1024;
   }
   const int n_tiles = (g.C_out + n_tile - 1) / n_tile;
-  dim3 grid((g.P_out + TC_BM - 1) / TC_BM, n_tiles);
+  // Optional 2-D pixel patches (CTB_TC_TILE2D=1) when they tile the map exactly.  Measured on B200: no gain -- the
+  // DCN gather at 128x128 went 150 -> 156 us, level1 184 -> 207 us -- the gather is not L1-capacity bound; off.
+  static const int tile2d_env = getenv("CTB_TC_TILE2D") ? atoi(getenv("CTB_TC_TILE2D")) : 0;
+  a.tiles_x = a.tiles_y = 0;
+  int m_tiles = (g.P_out + TC_BM - 1) / TC_BM;
+  if (tile2d_env && g.OW % 16 == 0 && g.OH % 8 == 0) {
+    a.tiles_x = g.OW / 16;
+    a.tiles_y = g.OH / 8;
+    m_tiles = g.B * a.tiles_x * a.tiles_y;
+  }
+  dim3 grid(m_tiles, n_tiles);
   conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(a);
   return after_launch();
 }

@@ -206,6 +206,68 @@ __global__ void upsample_add_kernel(const T* __restrict__ x, const T* __restrict
   }
 }
 
+// Same operator, weights held in registers: an output pixel's 2x2 taps depend only on its phase (oy mod f, ox mod f),
+// so blockIdx.y = phase, a thread keeps one channel vector's 4 x V tap weights for its whole lifetime and walks the
+// pixels of that phase (8 lanes x 16 B = one 128-byte line per pixel at C = 64): 4 input loads + 1 skip load per
+// output vector instead of 4 + 8 weight loads + 1.  Accumulation order = upsample_add_kernel's (bit-identical).
+template <typename T>
+__global__ void __launch_bounds__(256)
+upsample_add_phase_kernel(const T* __restrict__ x, const T* __restrict__ skip, const float* __restrict__ w,
+                          T* __restrict__ out, int B, int H, int W, int C, int f, int ld_in, int ld_skip, int ld_out) {
+  constexpr int V = VecIO<T>::N;
+  const int OW = W * f, OH = H * f, pad = f / 2, k = 2 * f, CV = C / V;
+  const int py = blockIdx.y / f, px = blockIdx.y - py * f;
+  const int cg = threadIdx.x % CV, c = cg * V;
+  const int dyh = (py + pad) / f, ky0 = (py + pad) - dyh * f;     // taps: (iy = m + dyh, ky0), (iy - 1, ky0 + f)
+  const int dxh = (px + pad) / f, kx0 = (px + pad) - dxh * f;
+  float wr[2][2][V];
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const int ky = ky0 + dy * f, kx = kx0 + dx * f;
+      const float* wp = w + ((size_t)ky * k + kx) * C + c;
+#pragma unroll
+      for (int q = 0; q < V; q += 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(wp + q));
+        wr[dy][dx][q] = t.x; wr[dy][dx][q + 1] = t.y; wr[dy][dx][q + 2] = t.z; wr[dy][dx][q + 3] = t.w;
+      }
+    }
+  const int slots = blockDim.x / CV;
+  const int total = B * H * W;
+  for (int j = blockIdx.x * slots + threadIdx.x / CV; j < total; j += gridDim.x * slots) {
+    const int n = j % W;
+    const int t = j / W;
+    const int m = t % H, b = t / H;
+    const int oy = m * f + py, ox = n * f + px;
+    float acc[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) acc[q] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const int iy = m + dyh - dy;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int ix = n + dxh - dx;
+        if (ix < 0 || ix >= W) continue;
+        float xv[V];
+        VecIO<T>::ld(x + (((size_t)b * H + iy) * W + ix) * ld_in + c, xv);
+#pragma unroll
+        for (int q = 0; q < V; ++q) acc[q] = fmaf(xv[q], wr[dy][dx][q], acc[q]);
+      }
+    }
+    const size_t op = ((size_t)b * OH + oy) * OW + ox;
+    if (skip) {
+      float sv[V];
+      VecIO<T>::ld(skip + op * ld_skip + c, sv);
+#pragma unroll
+      for (int q = 0; q < V; ++q) acc[q] += sv[q];
+    }
+    VecIO<T>::st(out + op * ld_out + c, acc);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // pre_hm splat: draw_umich_gaussian image.py:128-154 (gaussian2D in float64, np.maximum)
 // ------------------------------------------------------------------------------------------
@@ -290,6 +352,24 @@ extern "C" int ct_upsample_add(const void* x, const void* skip, const float* w, 
              "channels / strides must be multiples of the 16-byte vector width");
   const size_t total = (size_t)B * H * f * W * f * (C / vec);
   cudaStream_t st = (cudaStream_t)stream;
+  const int cv = C / vec;
+  if (cv <= 256 && 256 % cv == 0 && (size_t)B * H * W < (1u << 30)) {
+    // phase kernel: grid.y = f*f phases, grid.x sized so that all phases together fill the GPU a few times over
+    const int slots = 256 / cv;
+    int gx = (int)(((size_t)B * H * W + slots - 1) / slots);
+    const int cap = (148 * 8 + f * f - 1) / (f * f);
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, f * f);
+    if (dtype == CT_F32)
+      upsample_add_phase_kernel<float><<<grid, 256, 0, st>>>(
+          (const float*)x, (const float*)skip, w, (float*)out, B, H, W, C, f, ld_in, ld_skip, ld_out);
+    else
+      upsample_add_phase_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
+          (const __nv_bfloat16*)x, (const __nv_bfloat16*)skip, w, (__nv_bfloat16*)out, B, H, W, C, f,
+          ld_in, ld_skip, ld_out);
+    return after_launch();
+  }
   if (dtype == CT_F32)
     upsample_add_kernel<float><<<ew_blocks(total), 256, 0, st>>>(
         (const float*)x, (const float*)skip, w, (float*)out, B, H, W, C, f, ld_in, ld_skip, ld_out);

@@ -69,6 +69,8 @@ def conv_cases():
       ('1x1 448->128 slice of concat', 1, 448, 128, 16, 24, 1, 1, False, 64, 32),
       ('3x3 s1 256->512 (2 n-tiles)', 1, 256, 512, 8, 12, 3, 1, True, 0, 0),
       ('3x3 s1 64->1024 (heads.0)', 1, 64, 1024, 16, 24, 3, 1, False, 0, 0),
+      ('3x3 s2 32->64 (2-D pixel patches)', 2, 32, 64, 32, 64, 3, 2, False, 0, 0),
+      ('3x3 s1 64->64 +res (2-D pixel patches)', 2, 64, 64, 16, 32, 3, 1, True, 16, 0),
   ]
 
 

@@ -70,7 +70,7 @@ def test_head_1x1_writes_reference_layout_with_fused_activation(eng, cout_act):
 
 @pytest.mark.parametrize('eng', [ENGINES[0], ENGINES[2]], ids=['simt_f32', 'tcgen05'])
 @pytest.mark.parametrize('shape', [(1, 64, 64, 24, 40), (2, 128, 64, 16, 16), (1, 256, 256, 8, 12),
-                                   (1, 512, 256, 4, 6), (1, 64, 64, 5, 7)])
+                                   (1, 512, 256, 4, 6), (1, 64, 64, 5, 7), (2, 64, 64, 24, 32)])
 def test_dcn_v2(eng, shape):
   """Offset/mask conv + modulated deformable conv; large offsets push samples across and beyond the
   border (zero padding, partial bilinear weights)."""
@@ -192,7 +192,7 @@ def test_maxpool_and_upsample_add(dtype):
   ref = F.max_pool2d(x.float(), 2, 2)
   assert torch.equal(out[..., 8:40].permute(0, 3, 1, 2).float().cpu(), ref)
   assert float(out[..., :8].abs().max()) == 0 and float(out[..., 40:].abs().max()) == 0
-  for f in (2, 4):
+  for f in (2, 4, 8):
     w = torch.rand(32, 1, 2 * f, 2 * f, generator=g)
     skip = torch.randn(2, 32, 12 * f, 20 * f, generator=g).to(dtype)
     o = torch.empty(2, 12 * f, 20 * f, 32, dtype=dtype, device='cuda')
