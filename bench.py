@@ -137,6 +137,9 @@ def main():
   dev = torch.device('cuda', local)
   dist = None
   if world > 1:
+    # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION in some images) off it
+    if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+      os.environ['NCCL_DEBUG'] = 'WARN'
     import torch.distributed as dist
     dist.init_process_group('nccl', device_id=dev)
 
