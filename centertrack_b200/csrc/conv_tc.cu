@@ -239,7 +239,7 @@ conv_tc_kernel(const TcArgs a) {
     int row_off[TC_NROW], row_iy[TC_NROW], row_ix[TC_NROW];   // element offset / coords of the window's top-left input pixel
 #pragma unroll
     for (int i = 0; i < TC_NROW; ++i) {
-      const int p = tc_pixel(a, mt, r0 + 32 * i);
+      const int p = a.a_mode == CT_A_DCN ? g.P_out : tc_pixel(a, mt, r0 + 32 * i);   // DCN rows come from its table
       if (p < g.P_out) {
         const int b = p / HWo, r = p - b * HWo;
         const int oy = r / g.OW, ox = r - oy * g.OW;

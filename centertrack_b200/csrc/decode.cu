@@ -148,23 +148,22 @@ decode_kernel(DecodeArgs a) {
   // ------------------------------ phase 1: one plane ------------------------------
   {
     float* sp = reinterpret_cast<float*>(smem_raw);
-    unsigned* keep = reinterpret_cast<unsigned*>(smem_raw + (size_t)HW * 4);
     const float* src = pl < d.C ? d.hm + ((size_t)b * d.C + pl) * HW
                                 : d.hm_hp + ((size_t)b * d.J + (pl - d.C)) * HW;
-    for (int i = tid; i < HW; i += DT) sp[i] = __ldg(src + i);
-    __syncthreads();
-    // keep bit per element; lanes own consecutive elements (conflict-free smem reads), the warp
-    // ballot is the 32-bit mask word of those 32 elements (DT is a multiple of 32)
-    for (int i = tid; i < (HW + DT - 1) / DT * DT; i += DT) {
-      const bool kp = i < HW && nms_keep(sp, i, H, W);
-      const unsigned bits = __ballot_sync(0xffffffffu, kp);
-      if ((tid & 31) == 0 && i < HW) keep[i >> 5] = bits;
+    if ((HW & 3) == 0 && (reinterpret_cast<size_t>(src) & 15) == 0) {
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      float4* d4 = reinterpret_cast<float4*>(sp);
+      for (int i = tid; i < (HW >> 2); i += DT) d4[i] = __ldg(s4 + i);
+    } else {
+      for (int i = tid; i < HW; i += DT) sp[i] = __ldg(src + i);
     }
+    if (tid == 0) peak_n = 0;
     __syncthreads();
+    // heat * keep as a sort key: -0.0 cannot occur for sigmoid outputs; clamp negatives (not produced by the
+    // reference path) to 0 so the unsigned key order stays valid.  Only the degenerate general path evaluates
+    // the 3x3 NMS through this function; the fast path below does it with rolling row maxima.
     auto keyfn = [&](int i) -> unsigned long long {
-      const float v = ((keep[i >> 5] >> (i & 31)) & 1u) ? sp[i] : 0.f;
-      // heat * keep: -0.0 cannot occur for sigmoid outputs; clamp negatives (not produced by the
-      // reference path) to 0 so the unsigned key order stays valid
+      const float v = nms_keep(sp, i, H, W) ? sp[i] : 0.f;
       const unsigned vb = v > 0.f ? __float_as_uint(v) : 0u;
       return ((unsigned long long)vb << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
     };
@@ -172,29 +171,57 @@ decode_kernel(DecodeArgs a) {
     // indices once and select over that short list; it is exact whenever there are >= K such peaks (zeros, which
     // the index-ordered tie rule would otherwise have to rank, are then out of the race).  Degenerate planes
     // (fewer than K positive peaks, or more than the list holds) take the general path over all H*W keys.
-    unsigned* plist = keep + ((HW + 31) / 32);
-    if (tid == 0) peak_n = 0;
-    __syncthreads();
-    for (int i = tid; i < (HW + DT - 1) / DT * DT; i += DT) {
-      const bool pk = i < HW && ((keep[i >> 5] >> (i & 31)) & 1u) && sp[i] > 0.f;
-      const unsigned m = __ballot_sync(0xffffffffu, pk);
-      if (m) {
-        int base = 0;
-        if ((tid & 31) == 0) base = atomicAdd(&peak_n, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (pk) {
-          const int slot = base + __popc(m & ((1u << (tid & 31)) - 1u));
-          if (slot < PEAK_CAP) plist[slot] = (unsigned)i;
+    // NMS + compaction in ONE pass: thread = one column of a band of rows; the 3-wide row maxima of the rows above /
+    // at / below roll through registers (3 conflict-free shared loads + 4 max per element, no division).
+    unsigned* plist = reinterpret_cast<unsigned*>(smem_raw + (size_t)HW * 4);
+    bool listed = false;
+    if (W <= DT) {
+      listed = true;
+      const int nb = DT / W;                               // bands of rows
+      const int band = tid / W, x = tid - band * W;
+      const int rpb = (H + nb - 1) / nb;                   // rows per band (same trip count for every thread)
+      const int y0 = band * rpb;
+      const bool col_ok = band < nb;
+      const float NEG = __int_as_float(0xff800000);
+      auto rowmax = [&](int y) -> float {
+        if (!col_ok || y < 0 || y >= H) return NEG;
+        const float* r = sp + y * W;
+        float m = r[x];
+        if (x > 0) m = fmaxf(m, r[x - 1]);
+        if (x + 1 < W) m = fmaxf(m, r[x + 1]);
+        return m;
+      };
+      float up = rowmax(y0 - 1), cur = rowmax(y0);
+      for (int j = 0; j < rpb; ++j) {
+        const int y = y0 + j;
+        const float dn = rowmax(y + 1);
+        const bool in = col_ok && y < H;
+        const float c = in ? sp[y * W + x] : 0.f;
+        const bool pk = in && c > 0.f && fmaxf(fmaxf(up, cur), dn) == c;
+        const unsigned m = __ballot_sync(0xffffffffu, pk);
+        if (m) {
+          int base = 0;
+          if ((tid & 31) == 0) base = atomicAdd(&peak_n, __popc(m));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (pk) {
+            const int slot = base + __popc(m & ((1u << (tid & 31)) - 1u));
+            if (slot < PEAK_CAP) plist[slot] = (unsigned)(y * W + x);
+          }
         }
+        up = cur; cur = dn;
       }
     }
     __syncthreads();
     const int npk = peak_n;
-    const bool fast = npk >= K && npk <= PEAK_CAP;
+    const bool fast = listed && npk >= K && npk <= PEAK_CAP;
     if (tid == 0) sel_n = 0;
     for (int i = tid; i < a.kpad; i += DT) sel[i] = 0ull;
     if (fast) {
-      auto keyfn_l = [&](int j) -> unsigned long long { return keyfn((int)plist[j]); };
+      // listed elements are kept positive peaks: their key needs no NMS test
+      auto keyfn_l = [&](int j) -> unsigned long long {
+        const unsigned i = plist[j];
+        return ((unsigned long long)__float_as_uint(sp[i]) << 32) | (unsigned long long)(0xFFFFFFFFu - i);
+      };
       radix_select(npk, K, keyfn_l, hist, &ss);
       const unsigned long long prefix = ss.prefix, mask = ss.mask;
       for (int j = tid; j < npk; j += DT) {
@@ -401,7 +428,7 @@ extern "C" int ct_decode(const ct_decode_desc* d, void* stream) {
   while (kpad < d->K) kpad <<= 1;
   a.kpad = kpad;
   const int HW = d->H * d->W, K = d->K, J = a.d.J;
-  size_t smem1 = (size_t)HW * 4 + (size_t)((HW + 31) / 32) * 4 + (size_t)PEAK_CAP * 4;
+  size_t smem1 = (size_t)HW * 4 + (size_t)PEAK_CAP * 4;
   size_t smem2 = (size_t)(7 * K + 4 * J * K) * 4;
   size_t smem = smem1 > smem2 ? smem1 : smem2;
   if (smem > 200 * 1024)
