@@ -60,5 +60,9 @@ __device__ __forceinline__ float sigmoidf_ref(float x) {
   // same formula as ATen's CPU/CUDA sigmoid: 1 / (1 + exp(-x)), fp32, IEEE division
   return 1.0f / (1.0f + expf(-x));
 }
+// Branch-free variant for the tensor-core engines' epilogues (ex2.approx + rcp.approx, ~2 ulp): the IEEE division
+// and full-range expf of sigmoidf_ref form a ~130-cycle dependent chain per element that the two epilogue warps
+// per scheduler cannot hide (the 80-channel heat-map head spent 13k cycles per 128-pixel tile in it).
+__device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 }  // namespace ctb

@@ -218,7 +218,7 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // folded-BN shift / bias of this CTA's output-channel tile, staged once (read as float4 broadcasts)
-  float* s_shift = reinterpret_cast<float*>(sm + off_bar + 128);      // barriers + TMEM slot use < 128 bytes
+  float* s_shift = reinterpret_cast<float*>(sm + off_bar + 256);      // barriers + TMEM slot use < 256 bytes (S <= 4)
   {
     const int n0s = (blockIdx.x % a.n_tiles_n) * a.n_tile;
     for (int j = tid; j < 256; j += H_THREADS)
@@ -276,7 +276,7 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
     const uint32_t b_lo0 = (uint32_t)h_sdesc(sW, (uint32_t)a.n_tile * 16u, 128u);
     const uint32_t b_step = ((uint32_t)a.n_tile * 32u) >> 4;          // descriptor start-address units (16 B)
     // per-warp table of A-descriptor low words for halo stage 0 (walk: ky, kx|pair, chunk, K-step)
-    uint32_t* a_tab = reinterpret_cast<uint32_t*>(sm + off_bar + 128 + 1024) + (warp - 9) * 160;
+    uint32_t* a_tab = reinterpret_cast<uint32_t*>(sm + off_bar + 256 + 1024) + (warp - 9) * 160;
     for (int blk = lane; blk < a.nblk; blk += 32) {
       int r = blk;
       const int q = r % a.m_nq; r /= a.m_nq;
@@ -445,7 +445,7 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               if (g.relu) v[j] = fmaxf(v[j], 0.f);
-              if (o0 + j >= g.sig_from) v[j] = sigmoidf_ref(v[j]);
+              if (o0 + j >= g.sig_from) v[j] = sigmoidf_fast(v[j]);
             }
             if (o0 + 16 <= g.ld_out && (g.ld_out & 3) == 0) {      // padded row: four 16-byte stores
 #pragma unroll
@@ -462,7 +462,7 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
               if (o0 + j < g.C_out) {
                 float t = v[j];
                 if (g.relu) t = fmaxf(t, 0.f);
-                op[(size_t)j * HWo] = head_transform(t, g.head_act, g.depth_scale);
+                op[(size_t)j * HWo] = head_transform_fast(t, g.head_act, g.depth_scale);
               }
             }
           }
@@ -581,19 +581,37 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
   a.tiles_y = (g.OH + HT_H - 1) / HT_H;
   a.tiles_total = g.B * a.tiles_x * a.tiles_y;
   int cols = 32;
-  // One accumulator per MMA warp.  (Two per warp -- CTB_HALO_NACC=4 -- lets a warp run ahead of the epilogue and
-  // is ~15 % faster on the 64-channel layers, but showed a rare hang / wrong tile under stress on the TMA-heavy
-  // 1x1 heads (tools/repro_head.py); not enabled until that interaction is understood.)
-  a.nacc = 2;
+  // Two accumulators per MMA warp when TMEM allows (warp w owns accumulators w and w + 2): a warp can start its next
+  // item while the epilogue still drains the previous one (~15 % on the 64-channel layers).
+  a.nacc = 4 * n_tile <= 512 ? 4 : 2;
   { const char* e1 = getenv("CTB_HALO_NACC"); if (e1) a.nacc = atoi(e1); }
   { const char* e2 = getenv("CTB_HALO_MMA_WARPS"); a.mma_warps = e2 ? atoi(e2) : 2; }
   while (cols < a.nacc * n_tile) cols <<= 1;
   if (cols > 512) return fail(CT_ERR_INVALID, "conv_halo: n_tile too large for double-buffered TMEM%s", "");
   a.tmem_cols = cols;
   const size_t halo_bytes = (size_t)a.planes * a.plane_bytes;
-  int stages = 3;
-  auto smem_for = [&](int s) { return (size_t)((a.w_bytes + 1023) & ~1023u) + s * halo_bytes + 128 + 1024 + 2 * 160 * 4 + 1024; };
-  while (stages > 2 && smem_for(stages) > 220 * 1024) --stages;
+  auto smem_for = [&](int s) { return (size_t)((a.w_bytes + 1023) & ~1023u) + s * halo_bytes + 256 + 1024 + 2 * 160 * 4 + 1024; };
+  auto ctas_for = [&](int s) {
+    int n = (int)((227 * 1024) / smem_for(s));
+    if (n > 512 / cols) n = 512 / cols;
+    return n > 2 ? 2 : n;                 // register file: 2 x 352 threads x 80 registers
+  };
+  // Halo stages.  With two MMA warps taking alternate items, every stage must always be consumed by the SAME warp
+  // (stage = item % S with S even): a warp that saw only every other phase of a stage's full-barrier could not tell
+  // "my item has landed" from "the other warp's previous item has not landed yet" (same phase parity) and would
+  // run its MMAs on a half-loaded tile -- observed as rare wrong tiles / hangs with S = 3.  Layers with few MMAs
+  // per item (1x1 heads: TMA-latency bound, want three stages in flight) use ONE MMA warp and any S instead.
+  int stages;
+  if (a.mma_warps == 2 && a.nblk <= 16) a.mma_warps = 1;
+  if (a.mma_warps == 2) {
+    stages = (smem_for(4) <= 220 * 1024 && ctas_for(4) == ctas_for(2)) ? 4 : 2;
+  } else {
+    stages = 3;
+    while (stages > 2 && smem_for(stages) > 220 * 1024) --stages;
+  }
+  { const char* e3 = getenv("CTB_HALO_STAGES"); if (e3) stages = atoi(e3); }
+  if (a.mma_warps == 2 && (stages & 1))
+    return fail(CT_ERR_INVALID, "conv_halo: two MMA warps need an even number of halo stages%s", "");
   if (smem_for(stages) > 227 * 1024)
     return fail(CT_ERR_UNSUPPORTED, "conv_halo: weights + halo do not fit in shared memory%s (%ld bytes)", "",
                 (long)smem_for(stages));

@@ -452,7 +452,7 @@ conv_tc_kernel(const TcArgs a) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           if (g.relu) v[j] = fmaxf(v[j], 0.f);
-          if (o0 + j >= g.sig_from) v[j] = sigmoidf_ref(v[j]);
+          if (o0 + j >= g.sig_from) v[j] = sigmoidf_fast(v[j]);
         }
         if (o0 + 16 <= g.ld_out && (g.ld_out & 3) == 0) {      // padded row: four 16-byte stores
 #pragma unroll
@@ -470,7 +470,7 @@ conv_tc_kernel(const TcArgs a) {
           if (o0 + j < g.C_out) {
             float t = v[j];
             if (g.relu) t = fmaxf(t, 0.f);
-            op[(size_t)j * HWo] = head_transform(t, g.head_act, g.depth_scale);
+            op[(size_t)j * HWo] = head_transform_fast(t, g.head_act, g.depth_scale);
           }
         }
       }

@@ -13,6 +13,7 @@ from centertrack_b200 import _lib as L       # noqa
 from gpu_helpers import run_conv             # noqa
 
 lib = L.lib()
+import os as _os
 cases = [('stem 7x7 8->48 sum3 512x512', 16, 8, 48, 512, 512, 7, False, 48),
          ('level0 16->16 512x512', 16, 16, 16, 512, 512, 3, False, 16),
          ('heads.0 64->1024 nt128 128x128', 16, 64, 1024, 128, 128, 3, False, 128),
@@ -25,6 +26,11 @@ cases = [('stem 7x7 8->48 sum3 512x512', 16, 8, 48, 512, 512, 7, False, 48),
          ('1x1 256->128 4 chunks 128x128', 16, 256, 128, 128, 128, 1, False, 128),
          ('5x5 64->64 (100 MMAs/item) 128x128', 16, 64, 64, 128, 128, 5, False, 64),
          ('5x5 64->16 128x128', 16, 64, 16, 128, 128, 5, False, 16)]
+HEADS = [('head hm 1x1 256->80 NCHW f32 sigmoid', 16, 256, 80, 128, 128, 1, False, 80),
+         ('head wh 1x1 256->2 NCHW f32', 16, 256, 2, 128, 128, 1, False, 16),
+         ('offset 64->27 nt32 128x128 f32 NHWC', 16, 64, 27, 128, 128, 3, False, 32)]
+if _os.environ.get('TRACE_SET') == 'heads':
+  cases = HEADS
 g = torch.Generator().manual_seed(0)
 for (name, B, Cin, Cout, H, W, k, res, nt) in cases:
   x = torch.randn(B, Cin, H, W, generator=g)
@@ -34,6 +40,12 @@ for (name, B, Cin, Cout, H, W, k, res, nt) in cases:
   tr = torch.zeros(256 * 8, dtype=torch.int64, device='cuda')
   kw = dict(n_tile=nt, sum3=7) if Cin == 8 else dict(n_tile=nt)
   relu = Cin != 8
+  if name.startswith('head'):
+    kw.update(out_mode=L.CT_OUT_NCHW_F32, head_act=1 if 'sigmoid' in name else 0)
+    relu = False
+  if 'f32 NHWC' in name:
+    kw.update(out_mode=L.CT_OUT_NHWC_F32, sig_from=18)
+    relu = False
   run_conv(L.CT_ENGINE_TCGEN05_HALO, L.CT_BF16, x.cuda(), w, b, 1, relu, r, **kw)     # warm
   L.check(lib.ct_debug_trace(C.c_void_p(tr.data_ptr())))
   run_conv(L.CT_ENGINE_TCGEN05_HALO, L.CT_BF16, x.cuda(), w, b, 1, relu, r, **kw)
