@@ -550,6 +550,12 @@ int conv_forward_tc(const ct_conv_desc* d, cudaStream_t st) {
   };
   int stages = 4;                                   // keep >= 2 CTAs per SM when the tile allows it
   if (smem_for(stages) > 112 * 1024) stages = 3;
+  if (d->a_mode == CT_A_DCN) {
+    // the DCN gather, not the MMA, paces the pipeline: fewer stages leave more of the SM's 228 KB to L1, which
+    // the bilinear corner reads (each input pixel is touched ~36 times) depend on
+    static const int dcn_stages = getenv("CTB_TC_DCN_STAGES") ? atoi(getenv("CTB_TC_DCN_STAGES")) : 2;
+    if (dcn_stages >= 2 && dcn_stages < stages) stages = dcn_stages;
+  }
   if (stages > a.k_slices) stages = a.k_slices;
   a.stages = stages;
   const size_t smem = smem_for(stages);
