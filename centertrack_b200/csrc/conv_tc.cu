@@ -237,17 +237,37 @@ conv_tc_kernel(const TcArgs a) {
     const uint32_t swz = (uint32_t)((q ^ (r0 & 7)) << 4);
     const int HWo = g.OH * g.OW;
     int row_off[TC_NROW], row_iy[TC_NROW], row_ix[TC_NROW];   // element offset / coords of the window's top-left input pixel
+    if (a.a_mode == CT_A_DCN || a.tiles_x != 0) {
 #pragma unroll
-    for (int i = 0; i < TC_NROW; ++i) {
-      const int p = a.a_mode == CT_A_DCN ? g.P_out : tc_pixel(a, mt, r0 + 32 * i);   // DCN rows come from its table
-      if (p < g.P_out) {
-        const int b = p / HWo, r = p - b * HWo;
-        const int oy = r / g.OW, ox = r - oy * g.OW;
-        row_iy[i] = oy * g.stride - g.pad;
-        row_ix[i] = ox * g.stride - g.pad;
-        row_off[i] = (b * g.H * g.W + row_iy[i] * g.W + row_ix[i]) * g.ld_in;
-      } else {
-        row_off[i] = 0; row_iy[i] = -100000; row_ix[i] = -100000;
+      for (int i = 0; i < TC_NROW; ++i) {
+        const int p = a.a_mode == CT_A_DCN ? g.P_out : tc_pixel(a, mt, r0 + 32 * i);   // DCN rows come from its table
+        if (p < g.P_out) {
+          const int b = p / HWo, r = p - b * HWo;
+          const int oy = r / g.OW, ox = r - oy * g.OW;
+          row_iy[i] = oy * g.stride - g.pad;
+          row_ix[i] = ox * g.stride - g.pad;
+          row_off[i] = (b * g.H * g.W + row_iy[i] * g.W + row_ix[i]) * g.ld_in;
+        } else {
+          row_off[i] = 0; row_iy[i] = -100000; row_ix[i] = -100000;
+        }
+      }
+    } else {
+      // linear tiles: one division pair for the first row, the other rows (+32 pixels each) by carry propagation
+      int p = mt * TC_BM + r0;
+      int b = p / HWo, r = p - b * HWo;
+      int oy = r / g.OW, ox = r - oy * g.OW;
+#pragma unroll
+      for (int i = 0; i < TC_NROW; ++i) {
+        if (p < g.P_out) {
+          row_iy[i] = oy * g.stride - g.pad;
+          row_ix[i] = ox * g.stride - g.pad;
+          row_off[i] = (b * g.H * g.W + row_iy[i] * g.W + row_ix[i]) * g.ld_in;
+        } else {
+          row_off[i] = 0; row_iy[i] = -100000; row_ix[i] = -100000;
+        }
+        p += 32; ox += 32;
+        while (ox >= g.OW) { ox -= g.OW; ++oy; }
+        while (oy >= g.OH) { oy -= g.OH; ++b; }
       }
     }
     if (tid == 0) tc_stamp(1);
@@ -418,8 +438,17 @@ conv_tc_kernel(const TcArgs a) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
       if (a.shift) {
+        if (o0 + 16 <= g.C_out && (reinterpret_cast<size_t>(a.shift + o0) & 15) == 0) {   // four 16-byte loads
+          const float4* sh4 = reinterpret_cast<const float4*>(a.shift + o0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) if (o0 + j < g.C_out) v[j] += __ldg(a.shift + o0 + j);
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 sh = __ldg(sh4 + j4);
+            v[4 * j4] += sh.x; v[4 * j4 + 1] += sh.y; v[4 * j4 + 2] += sh.z; v[4 * j4 + 3] += sh.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (o0 + j < g.C_out) v[j] += __ldg(a.shift + o0 + j);
+        }
       }
       if (g.out_mode == CT_OUT_NHWC) {
         if (a.residual) {
