@@ -3,8 +3,10 @@ on one GPU (streams shard across GPUs, replicas of the weights, no da
 
 One step = for every stream its current frame: network (pre_img = that stream's previous frame, kept on
 the device exactly like detector.py:148) + fused sigmoid + fused decode -> one packed record buffer
-[B,K,F].  Two input slots alternate, so step t's images are step t+1's pre_images without a copy, and
-two CUDA graphs (one per slot parity) replay the whole step as a single launch each.
+[B,K,F].  THREE input slots rotate: step t reads slot t%3 (images) and slot (t-1)%3 (pre_images: the previous
+step's images, never copied) while the copy stream uploads step t+1's frames into slot (t+1)%3 -- with two slots
+the upload would have to wait for the step that still reads its target as pre_images.  One CUDA graph per slot
+replays the whole step as a single launch.
 
 The end-to-end form (`step_host`) takes HOST frames: pinned staging, H2D on a copy stream overlapped
 with the previous step's compute, graph replay, D2H of the records.
@@ -18,6 +20,9 @@ from . import _lib as L
 from .decode import generic_decode
 
 
+NS = 3          # input slots
+
+
 class StreamRunner(object):
 
   def __init__(self, model, B, H, W, K=100, precision='bf16', device='cuda', use_graph=True):
@@ -27,18 +32,18 @@ class StreamRunner(object):
     self.eng = model.engine_for(B, H, W, self.device, precision)
     self.eng.set_fused_activations(True)
     f32 = torch.float32
-    self.img = [torch.zeros((B, 3, H, W), dtype=f32, device=self.device) for _ in range(2)]
-    self.hm = [torch.zeros((B, 1, H, W), dtype=f32, device=self.device) for _ in range(2)]
-    self.h_img = [torch.zeros((B, 3, H, W), dtype=f32).pin_memory() for _ in range(2)]
-    self.h_hm = [torch.zeros((B, 1, H, W), dtype=f32).pin_memory() for _ in range(2)]
+    self.img = [torch.zeros((B, 3, H, W), dtype=f32, device=self.device) for _ in range(NS)]
+    self.hm = [torch.zeros((B, 1, H, W), dtype=f32, device=self.device) for _ in range(NS)]
+    self.h_img = [torch.zeros((B, 3, H, W), dtype=f32).pin_memory() for _ in range(NS)]
+    self.h_hm = [torch.zeros((B, 1, H, W), dtype=f32).pin_memory() for _ in range(NS)]
     self.rec = None
     self.layout = None
     self.use_graph = use_graph
-    self.graphs = [None, None]
+    self.graphs = [None] * NS
     self.compute = torch.cuda.Stream(device=self.device)
     self.copy = torch.cuda.Stream(device=self.device)
-    self.ev_in = [torch.cuda.Event() for _ in range(2)]      # slot uploaded
-    self.ev_done = [torch.cuda.Event() for _ in range(2)]    # slot's step finished (inputs reusable)
+    self.ev_in = [torch.cuda.Event() for _ in range(NS)]     # slot uploaded
+    self.ev_done = [torch.cuda.Event() for _ in range(NS)]   # slot no longer read (neither as images nor pre_images)
     self.t = 0
     self._eager(0)                                           # sizes the record buffer
     torch.cuda.synchronize(self.device)
@@ -47,7 +52,7 @@ class StreamRunner(object):
 
   # one step, eager launches on the current stream
   def _eager(self, slot):
-    out = dict(self.eng.forward(self.img[slot], self.img[1 - slot], self.hm[slot]))
+    out = dict(self.eng.forward(self.img[slot], self.img[(slot - 1) % NS], self.hm[slot]))
     res = generic_decode(out, K=self.K, records_out=self.rec)
     if self.rec is None:
       self.rec, self.layout = res.records, res.layout
@@ -67,7 +72,7 @@ class StreamRunner(object):
     return self.graphs[slot]
 
   def warm(self):
-    for s in (0, 1):
+    for s in range(NS):
       if self.use_graph:
         self._graph(s)
       else:
@@ -80,7 +85,7 @@ class StreamRunner(object):
 
   def step_device(self):
     """Inputs already resident in the slot buffers; runs on the current stream."""
-    slot = self.t & 1
+    slot = self.t % NS
     if self.use_graph:
       self._graph(slot).replay()
     else:
@@ -92,14 +97,14 @@ class StreamRunner(object):
     """images [B,3,H,W], pre_hms [B,1,H,W]: float32 HOST tensors (what Detector.pre_process /
     _get_additional_inputs produce).  Returns the records of the PREVIOUS call (None the first time) --
     a one-step software pipeline: this step's H2D overlaps the previous step's compute."""
-    slot = self.t & 1
+    slot = self.t % NS
     src_img, src_hm = images, pre_hms
     if not (images.is_pinned() and pre_hms.is_pinned()):   # pageable input: stage through pinned memory
       self.h_img[slot].copy_(images)
       self.h_hm[slot].copy_(pre_hms)
       src_img, src_hm = self.h_img[slot], self.h_hm[slot]
     with torch.cuda.stream(self.copy):
-      self.copy.wait_event(self.ev_done[slot])       # slot's old contents no longer needed (as pre_img of t-1)
+      self.copy.wait_event(self.ev_done[slot])       # slot's old contents were last read as pre_images of step t-2
       self.img[slot].copy_(src_img, non_blocking=True)
       self.hm[slot].copy_(src_hm, non_blocking=True)
       self.ev_in[slot].record(self.copy)
@@ -110,9 +115,9 @@ class StreamRunner(object):
         self._graph(slot).replay()
       else:
         self._eager(slot)
-      self.h_rec[slot].copy_(self.rec, non_blocking=True)
-      # the OTHER slot (this step's pre_images) may be overwritten once this step is done
-      self.ev_done[1 - slot].record(self.compute)
+      self.h_rec[self.t & 1].copy_(self.rec, non_blocking=True)
+      # this step's pre_images slot may be overwritten once this step is done
+      self.ev_done[(slot - 1) % NS].record(self.compute)
     self.t += 1
     return prev
 
