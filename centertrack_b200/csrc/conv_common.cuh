@@ -63,12 +63,6 @@ __device__ __forceinline__ float head_transform(float v, int head_act, float dep
   return v;
 }
 
-__device__ __forceinline__ float head_transform_fast(float v, int head_act, float depth_scale) {
-  if (head_act == CT_HEAD_SIGMOID) return sigmoidf_fast(v);
-  if (head_act == CT_HEAD_DEPTH) return (__fdividef(1.f, sigmoidf_fast(v) + 1e-6f) - 1.f) * depth_scale;
-  return v;
-}
-
 int conv_forward_simt(const ct_conv_desc* d, cudaStream_t st);
 int conv_forward_tc(const ct_conv_desc* d, cudaStream_t st);
 int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st);

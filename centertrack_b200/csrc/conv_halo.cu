@@ -47,6 +47,7 @@ struct HaloArgs {
   const __nv_bfloat16* residual;
   void* out;
   int n_tile, n_tiles_n, nblk, planes, pw, ph, plane_bytes, box_bytes, halo_stages, tmem_cols;
+  int tw, th;                           // output tile: 8 x 16, or 32 x 4 for 1x1 convs writing NCHW planes
   int nacc;                             // TMEM accumulator stages (4 when 4*n_tile <= 512 columns, else 2)
   int mma_warps;                        // 2 (default) or 1 (debug: CTB_HALO_MMA_WARPS)
   int tiles_x, tiles_y, tiles_total;    // spatial tiles per image / total work items (incl. n tiles)
@@ -209,7 +210,7 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
   if (tid == 0) {
     h_mbar_init(w_full, 1);
     for (int s = 0; s < S; ++s) { h_mbar_init(halo_full(s), 1); h_mbar_init(halo_empty(s), 1); }
-    for (int s = 0; s < 4; ++s) { h_mbar_init(tmem_full(s), 1); h_mbar_init(tmem_empty(s), 32 * H_EPI_WARPS); }
+    for (int s = 0; s < 4; ++s) { h_mbar_init(tmem_full(s), 1); h_mbar_init(tmem_empty(s), H_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 9) {
@@ -251,7 +252,7 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
         h_stamp(it, 0);
         const int b = sp / per_img, r = sp - b * per_img;
         const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
-        const int x0 = tx * HT_W - g.pad, y0 = ty * HT_H - g.pad;
+        const int x0 = tx * a.tw - g.pad, y0 = ty * a.th - g.pad;
         h_mbar_expect_tx(halo_full(s), (uint32_t)(a.planes * a.box_bytes));   // TMA writes the full box (zero fill incl.)
         if (a.merged_xc) {
           h_tma_3d(sH + s * halo_bytes, &tmap, x0 * 8, y0, b, halo_full(s));
@@ -327,7 +328,9 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
     // ===================== epilogue warps 0..7 =====================
     const int wq = warp & 3, chalf = warp >> 2;
     const int row = wq * 32 + lane;              // GEMM row = g*8 + r  ->  pixel (ty*16 + g, tx*8 + r)
-    const int gy = row >> 3, rx = row & 7;
+    // 8 consecutive GEMM rows = 8 consecutive x; the 8-row groups then run along x (tw / 8 of them) before y
+    const int gpr = a.tw >> 3;
+    const int gy = (row >> 3) / gpr, rx = (((row >> 3) % gpr) << 3) | (row & 7);
     const int HWo = g.OH * g.OW;
     // Residual tiles are prefetched one work item ahead into registers (the load does not depend on the MMA):
     // issued right after the previous item consumed its copy, they land while this warp waits for the next
@@ -338,7 +341,7 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
     auto prefetch_residual = [&](int sp_n) {
       const int bn = sp_n / per_img, rn = sp_n - bn * per_img;
       const int tyn = rn / a.tiles_x, txn = rn - tyn * a.tiles_x;
-      const int oyn = tyn * HT_H + gy, oxn = txn * HT_W + rx;
+      const int oyn = tyn * a.th + gy, oxn = txn * a.tw + rx;
       const bool okn = oyn < g.OH && oxn < g.OW;
       const size_t pn = ((size_t)bn * g.OH + oyn) * g.OW + oxn;
 #pragma unroll
@@ -358,7 +361,7 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
       const uint32_t pa = (uint32_t)(it / NACC) & 1u;
       const int b = sp / per_img, r = sp - b * per_img;
       const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
-      const int oy = ty * HT_H + gy, ox = tx * HT_W + rx;
+      const int oy = ty * a.th + gy, ox = tx * a.tw + rx;
       const bool p_ok = oy < g.OH && ox < g.OW;
       const size_t p = ((size_t)b * g.OH + oy) * g.OW + ox;
       h_mbar_wait(tmem_full(acc), pa, 5, it);
@@ -394,6 +397,7 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
         for (int col = chalf * 16; col < a.n_tile; col += 32) {
           uint32_t rr[16];
           h_ld16(t_lane + (uint32_t)col, rr);
+          if (tid == 0 && col == 0) h_stamp(it, 7);
           const int o0 = n0 + col;
           if (!p_ok || o0 >= g.C_out) continue;
           float v[16];
@@ -445,7 +449,8 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               if (g.relu) v[j] = fmaxf(v[j], 0.f);
-              if (o0 + j >= g.sig_from) v[j] = sigmoidf_fast(v[j]);
+              const float sg = sigmoidf_fast(v[j]);            // unconditional: keeps the 16 chains interleaved
+              v[j] = (o0 + j >= g.sig_from) ? sg : v[j];
             }
             if (o0 + 16 <= g.ld_out && (g.ld_out & 3) == 0) {      // padded row: four 16-byte stores
 #pragma unroll
@@ -457,20 +462,29 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
             }
           } else {
             float* op = reinterpret_cast<float*>(a.out) + ((size_t)b * g.C_out + o0) * HWo + (size_t)oy * g.OW + ox;
+            // transform all 16 values in straight-line code (the activation kind is uniform: hoisted out of the
+            // loop), then the guarded stores -- per-element branches serialise the ex2/rcp chains (~190 cycles each)
+            if (g.relu) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (o0 + j < g.C_out) {
-                float t = v[j];
-                if (g.relu) t = fmaxf(t, 0.f);
-                op[(size_t)j * HWo] = head_transform_fast(t, g.head_act, g.depth_scale);
-              }
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
             }
+            if (g.head_act == CT_HEAD_SIGMOID) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = sigmoidf_fast(v[j]);
+            } else if (g.head_act == CT_HEAD_DEPTH) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = (__fdividef(1.f, sigmoidf_fast(v[j]) + 1e-6f) - 1.f) * g.depth_scale;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (o0 + j < g.C_out) op[(size_t)j * HWo] = v[j];
           }
         }
       }
       if (use_res && sp + sp_stride < sp_total) prefetch_residual(sp + sp_stride);
       h_fence_before();
-      h_mbar_arrive(tmem_empty(acc));      // all epilogue threads arrive: frees this accumulator stage
+      __syncwarp();
+      if (lane == 0) h_mbar_arrive(tmem_empty(acc));      // one arrival per epilogue warp frees the accumulator
       if (tid == 0) h_stamp(it, 6);
     }
   }
@@ -554,8 +568,16 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
                                                 // shared-memory address (same as the TMA's), no base offset needed
   a.merged_xc = (g.C_in == 8 && g.ld_in == 8) ? 1 : 0;
   a.planes = a.swz ? (g.C_in * 2 + a.swz - 1) / a.swz : g.C_in / 8;   // swizzled: 64-channel chunks
-  a.pw = HT_W + g.KW - 1 + (a.pair_taps ? 1 : 0);
-  a.ph = HT_H + g.KH - 1;
+  // 1x1 convs writing fp32 NCHW planes (the 1x1 heads) use a 32 x 4 pixel tile: there is no halo, the TMA box
+  // [4][32][c] is already the canonical K-major operand (8-pixel groups 8 rows apart), and every epilogue warp then
+  // owns 32 consecutive x of one row: its per-channel store is one full 128-byte line instead of four 32-byte pieces.
+  a.tw = HT_W; a.th = HT_H;
+  static const int wide_env = getenv("CTB_HALO_WIDE") ? atoi(getenv("CTB_HALO_WIDE")) : 1;
+  if (wide_env && g.KH == 1 && g.KW == 1 && g.out_mode == CT_OUT_NCHW_F32 && a.swz && g.OW % 32 == 0 && g.OH % 4 == 0) {
+    a.tw = 32; a.th = 4;
+  }
+  a.pw = a.tw + g.KW - 1 + (a.pair_taps ? 1 : 0);
+  a.ph = a.th + g.KH - 1;
   a.box_bytes = a.pw * a.ph * (a.swz ? a.swz : 16);
   a.plane_bytes = (a.box_bytes + 1023) / 1024 * 1024;
   a.w_bytes = (uint32_t)a.nblk * n_tile * 32u;
@@ -570,15 +592,16 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
     a.m_sky = (uint32_t)a.pw * rb16; a.m_skx = rb16; a.m_sc = (uint32_t)a.plane_bytes >> 4; a.m_sq = 2;
     a.m_alo = 1u << 16;
     const uint32_t layout = a.swz == 128 ? 2u : (a.swz == 64 ? 4u : 6u);
-    a.m_ahi = ((uint32_t)a.pw * rb16) | (1u << 14) | (layout << 29);
+    const uint32_t sbo16 = a.tw == HT_W ? (uint32_t)a.pw * rb16 : 8u * rb16;     // next 8-row group: next tile row / next 8 px
+    a.m_ahi = sbo16 | (1u << 14) | (layout << 29);
   } else {
     a.m_nky = g.KH; a.m_nkx = g.KW; a.m_nc = 1; a.m_nq = g.C_in / 16;
     a.m_sky = a.pw; a.m_skx = 1; a.m_sc = 0; a.m_sq = 2u * ((uint32_t)a.plane_bytes >> 4);
     a.m_alo = ((uint32_t)a.plane_bytes >> 4) << 16;       // LBO = plane stride
     a.m_ahi = (uint32_t)a.pw | (1u << 14);
   }
-  a.tiles_x = (g.OW + HT_W - 1) / HT_W;
-  a.tiles_y = (g.OH + HT_H - 1) / HT_H;
+  a.tiles_x = (g.OW + a.tw - 1) / a.tw;
+  a.tiles_y = (g.OH + a.th - 1) / a.th;
   a.tiles_total = g.B * a.tiles_x * a.tiles_y;
   int cols = 32;
   // Two accumulators per MMA warp when TMEM allows (warp w owns accumulators w and w + 2): a warp can start its next

@@ -213,7 +213,7 @@ conv_tc_kernel(const TcArgs a) {
   if (tid == 0) tc_stamp(0);
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), TC_PRODUCERS); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), TC_PRODUCERS / 32); mbar_init(empty_bar(s), 1); }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -370,7 +370,8 @@ conv_tc_kernel(const TcArgs a) {
         blend_half(tap, stage, 1, vb);
         tap = ntap; cq = ncq;
         fence_proxy_async();
-        mbar_arrive(full_bar(stage));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar(stage));      // one arrival per producer warp
         if (tid == 0) tc_stamp(8 + s);
       }
     } else {
@@ -404,7 +405,9 @@ conv_tc_kernel(const TcArgs a) {
 #pragma unroll
         for (int i = 0; i < TC_NROW; ++i) sts16(dst + i * 4096u, v[i]);
         fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-        mbar_arrive(full_bar(stage));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar(stage));      // one arrival per producer warp (256 arrivals on one
+                                                          // shared-memory word serialise)
         if (tid == 0) tc_stamp(8 + s);
       };
       const int KS = a.k_slices;
@@ -481,7 +484,8 @@ conv_tc_kernel(const TcArgs a) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           if (g.relu) v[j] = fmaxf(v[j], 0.f);
-          if (o0 + j >= g.sig_from) v[j] = sigmoidf_fast(v[j]);
+          const float sg = sigmoidf_fast(v[j]);              // unconditional: keeps the 16 chains interleaved
+          v[j] = (o0 + j >= g.sig_from) ? sg : v[j];
         }
         if (o0 + 16 <= g.ld_out && (g.ld_out & 3) == 0) {      // padded row: four 16-byte stores
 #pragma unroll
@@ -494,14 +498,20 @@ conv_tc_kernel(const TcArgs a) {
       } else {
         const int b = p / HWo, rr = p - b * HWo;
         float* op = reinterpret_cast<float*>(a.out) + ((size_t)b * g.C_out + o0) * HWo + rr;
+        if (g.relu) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (o0 + j < g.C_out) {
-            float t = v[j];
-            if (g.relu) t = fmaxf(t, 0.f);
-            op[(size_t)j * HWo] = head_transform_fast(t, g.head_act, g.depth_scale);
-          }
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
         }
+        if (g.head_act == CT_HEAD_SIGMOID) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = sigmoidf_fast(v[j]);
+        } else if (g.head_act == CT_HEAD_DEPTH) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = (__fdividef(1.f, sigmoidf_fast(v[j]) + 1e-6f) - 1.f) * g.depth_scale;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (o0 + j < g.C_out) op[(size_t)j * HWo] = v[j];
       }
     }
   } else if (lane == 0) {

@@ -146,6 +146,18 @@ def test_halo_engine_fp32_outputs():
   got = run_conv(L.CT_ENGINE_TCGEN05_HALO, L.CT_BF16, x.cuda(), w, b, 1, relu=False, out_mode=L.CT_OUT_NCHW_F32,
                  head_act=1, n_tile=80)
   _close(got, ref, 1e-4)
+  # 32 x 4 pixel tiles (W % 32 == 0): the 1x1 heads at full resolution, 256 input channels in four chunks
+  x = torch.randn(2, 256, 8, 64, generator=g)
+  w = torch.randn(80, 256, 1, 1, generator=g) * 0.05
+  ref = torch.sigmoid(F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b))
+  got = run_conv(L.CT_ENGINE_TCGEN05_HALO, L.CT_BF16, x.cuda(), w, b, 1, relu=False, out_mode=L.CT_OUT_NCHW_F32,
+                 head_act=1, n_tile=80)
+  _close(got, ref, 2e-4)
+  w2 = torch.randn(2, 256, 1, 1, generator=g) * 0.05
+  ref = F.conv2d(x.bfloat16().float(), w2.bfloat16().float(), b[:2])
+  got = run_conv(L.CT_ENGINE_TCGEN05_HALO, L.CT_BF16, x.cuda(), w2, b[:2], 1, relu=False, out_mode=L.CT_OUT_NCHW_F32,
+                 n_tile=16)
+  _close(got, ref, 2e-3)
 
 
 @pytest.mark.parametrize('mask', [7, 1, 3])

@@ -65,6 +65,8 @@ for (name, B, Cin, Cout, H, W, k, res, nt) in cases:
     print('  issue phase per MMA: %.0f cycles (nblk %d); period per MMA %.0f' % (np.mean(t[2:n, 4] - t[2:n, 3]) / nblk, nblk, np.mean(np.diff(t[1:n, 4])) / nblk))
   if n > 4:
     d = t[2:n]
+    print('  first tcgen05.ld after the accumulator is ready: %.0f cycles; rest of the epilogue %.0f' % (
+        np.mean(d[:, 7] - d[:, 5]), np.mean(d[:, 6] - d[:, 7])))
     print('  mean over items 2..: wait_halo %.0f  wait_acc %.0f  issue %.0f  | epi %.0f | tma_latency(iss->mma_halo of same item) %.0f  period %.0f' % (
         np.mean(d[:, 2] - np.maximum(t[1:n - 1, 4], d[:, 2] * 0 + t[1:n - 1, 4])), np.mean(d[:, 3] - d[:, 2]), np.mean(d[:, 4] - d[:, 3]),
         np.mean(d[:, 6] - d[:, 5]), np.mean(d[:, 2] - d[:, 1]), np.mean(np.diff(t[1:n, 4]))))
