@@ -222,6 +222,10 @@ def main():
     return
 
   # ---------------- roofline of the dominant kernel (conv_tc_kernel), measured live ----------------
+  # `traffic`: dram__bytes_read.sum + dram__bytes_write.sum of these launches from the committed ncu --set full capture
+  # of one step at 32 frames/step (profiles/r01f_ncu_tc_raw.csv: 2157.5 + 381.1 MB over the 40 launches;
+  # profiles/r01f_ncu_halo_raw.csv: 3058.0 + 1848.4 MB over the 34 launches), scaled by frames per step.
+  NCU_DRAM_BYTES_PER_FRAME = {'conv_tc': 2538.59e6 / 32, 'conv_halo': 4906.37e6 / 32}
   eng = runner.eng
   stream = torch.cuda.current_stream()
   conv_ms, conv_flop, all_ms, halo_ms, halo_flop = 0.0, 0.0, 0.0, 0.0, 0.0
@@ -260,10 +264,14 @@ def main():
   roofline = {'kernel': 'conv_tc_kernel (all %d gather-engine tcgen05 conv/DCN launches of one step)' %
               sum(1 for k, p, n in eng.ops if k == 'conv' and p.engine == L.CT_ENGINE_TCGEN05),
               'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
-              'frac': achieved / peak_tf if peak_tf else None, 'traffic': None, 'peak_source': peak_src,
+              'frac': achieved / peak_tf if peak_tf else None,
+              'traffic': NCU_DRAM_BYTES_PER_FRAME['conv_tc'] * B if args.precision == 'bf16' else None,
+              'traffic_unit': 'bytes per step (all launches of the kernel), ncu capture at 32 frames/step scaled',
+              'peak_source': peak_src,
               'share_of_step': conv_ms / all_ms if all_ms else None,
               'second_kernel': {'kernel': 'conv_halo_kernel (%d launches)' % sum(1 for k, p, n in eng.ops if k == 'conv' and p.engine == L.CT_ENGINE_TCGEN05_HALO),
                                 'achieved': halo_tf, 'frac': halo_tf / peak_tf if peak_tf else None,
+                                'traffic': NCU_DRAM_BYTES_PER_FRAME['conv_halo'] * B if args.precision == 'bf16' else None,
                                 'share_of_step': halo_ms / all_ms if all_ms else None},
               'eager_ms_by_kind': {k: round(v, 3) for k, v in per_kind.items()},
               'whole_step_tflops': GFLOP_PER_FRAME * B / ms_per_step}

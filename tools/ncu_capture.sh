@@ -1,19 +1,21 @@
 #!/bin/bash
-# ncu --set full captures of one eager step (B=16), exported to CSV on the box (reports can exceed the 64 MiB
-# gpurun_out limit); per-instruction source pages for selected kernel instances.
+# Evidence captures for profiles/ (run on the GPU box):  bash tools/ncu_capture.sh <tag> [frames per step]
+#  1. launch list (gpu__time_duration) of the bench command itself
+#  2. ncu --set full of one eager step's conv_tc / conv_halo / decode launches, exported to CSV on the box
+#     (the .ncu-rep files can exceed the 64 MiB gpurun_out limit)
 mkdir -p gpurun_out
 TAG=${1:-r1}
-run() {  # name, kernel regex, skip, count, "ids for source export"
+B=${2:-32}
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches_bench.csv \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --batch $B > gpurun_out/${TAG}_bench_under_ncu.log 2>&1
+run() {  # name, kernel regex, skip, count
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$2" -s $3 -c $4 -f -o /tmp/$1 \
-      python tools/profile_step.py 16 2 > gpurun_out/ncu_$1.log 2>&1
-  ncu -i /tmp/$1.ncu-rep --page raw --csv > gpurun_out/${TAG}_$1_raw.csv 2>/dev/null
-  ncu -i /tmp/$1.ncu-rep --page details --csv > gpurun_out/${TAG}_$1_details.csv 2>/dev/null
-  for id in $5; do
-    ncu -i /tmp/$1.ncu-rep --page source --csv --kernel-id ::$2:$id 2>/dev/null | cut -d, -f1-12 > gpurun_out/${TAG}_$1_source_$id.csv
-  done
+      python tools/profile_step.py $B 2 > gpurun_out/ncu_$1.log 2>&1
+  ncu -i /tmp/$1.ncu-rep --page raw --csv > gpurun_out/${TAG}_ncu_$1_raw.csv 2>/dev/null
+  ncu -i /tmp/$1.ncu-rep --page details --csv > gpurun_out/${TAG}_ncu_$1_details.csv 2>/dev/null
   echo "$1: report $(stat -c %s /tmp/$1.ncu-rep 2>/dev/null) bytes"
 }
-run halo "conv_halo_kernel" 34 34 "35 36 41 49 67 68"
-run tc "conv_tc_kernel" 40 40 "41 61 73"
-run decode "decode_kernel" 1 1 "2"
-ls -la gpurun_out | tail -25
+run tc "conv_tc_kernel" 40 40
+run halo "conv_halo_kernel" 34 34
+run decode "decode_kernel" 1 1
+ls -la gpurun_out | tail -12
