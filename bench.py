@@ -112,7 +112,20 @@ def run_reference(args, rank, world):
                            'sample': '%d steps x %d frame (oracle/ct_oracle.py: torch-CPU fp32 convs + '
                                      'restated DCNv2/decode)' % (steps, frames_per_step)},
           'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-  print(json.dumps(line))
+  _emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _emit(line):
+  data = (json.dumps(line) + '\n').encode()
+  if _REAL_STDOUT is None:
+    sys.stdout.write(data.decode())
+    sys.stdout.flush()
+  else:
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -125,6 +138,12 @@ def main():
   ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
   ap.add_argument('--no-cpu-baseline', action='store_true')
   args = ap.parse_args()
+  # stdout carries exactly ONE JSON line: everything any library writes to fd 1 during the run (NCCL prints a version
+  # banner there) is sent to stderr, and the result line goes to the saved descriptor (see _emit)
+  global _REAL_STDOUT
+  sys.stdout.flush()
+  _REAL_STDOUT = os.dup(1)
+  os.dup2(2, 1)
   args.warmup = max(args.warmup, 3)
 
   rank = int(os.environ.get('RANK', 0))
@@ -137,9 +156,6 @@ def main():
   dev = torch.device('cuda', local)
   dist = None
   if world > 1:
-    # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION in some images) off it
-    if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-      os.environ['NCCL_DEBUG'] = 'WARN'
     import torch.distributed as dist
     dist.init_process_group('nccl', device_id=dev)
 
@@ -298,7 +314,7 @@ def main():
           'gpu_launches': int(runner.launches_per_step * args.steps),
           'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
           'check': {'top_score_frame0': float(rec_last[0, 0, 0])}}
-  print(json.dumps(line))
+  _emit(line)
   if dist is not None:
     dist.destroy_process_group()
 
