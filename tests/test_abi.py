@@ -35,14 +35,14 @@ def test_python_binding_lists_match_header(built_lib):
 
 
 def test_sass_is_blackwell_native(built_lib):
-  """tcgen05.mma / tcgen05.ld / TMA bulk copy must be in the SASS (UTCHMMA / LDTM / UBLKCP)."""
+  """tcgen05.mma / tcgen05.ld / TMA bulk copy must be in the SASS (UTCHMMA / LDTM / UBLKCP / UTMALDG tensor loads / UTCBAR commits)."""
   import shutil
   import subprocess
   if shutil.which('cuobjdump') is None:
     import pytest
     pytest.skip('cuobjdump not available')
   sass = subprocess.run(['cuobjdump', '-sass', built_lib], capture_output=True, text=True).stdout
-  for mnemonic in ('UTCHMMA', 'LDTM', 'UBLKCP'):
+  for mnemonic in ('UTCHMMA', 'LDTM', 'UBLKCP', 'UTMALDG', 'UTCBAR'):
     assert mnemonic in sass, mnemonic
 
 
