@@ -274,6 +274,19 @@ def main():
   halo_ms /= reps
   halo_flop /= reps
   all_ms /= reps
+  # decode-only latency: the fused NMS + top-K + gather launch on the maps the last step left in HBM
+  from centertrack_b200.decode import generic_decode
+  dec_out = dict(eng.forward(runner.img[0], runner.img[1], runner.hm[0]))
+  for _ in range(3):
+    generic_decode(dec_out, K=K, records_out=runner.rec)
+  d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  d0.record()
+  for _ in range(10):
+    generic_decode(dec_out, K=K, records_out=runner.rec)
+  d1.record()
+  torch.cuda.synchronize(dev)
+  decode_us = d0.elapsed_time(d1) * 1000.0 / 10
+  hm_bytes = float(dec_out['hm'].numel() * 4)
   peak_tf, peak_hbm, peak_src = _peaks()
   achieved = conv_flop / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
   halo_tf = halo_flop / (halo_ms / 1000.0) / 1e12 if halo_ms > 0 else 0.0
@@ -290,6 +303,9 @@ def main():
                                 'traffic': NCU_DRAM_BYTES_PER_FRAME['conv_halo'] * B if args.precision == 'bf16' else None,
                                 'share_of_step': halo_ms / all_ms if all_ms else None},
               'eager_ms_by_kind': {k: round(v, 3) for k, v in per_kind.items()},
+              'decode': {'us_per_launch': round(decode_us, 1), 'frames': B, 'bound': 'hbm',
+                         'achieved': hm_bytes / (decode_us * 1e-6) / 1e9, 'peak': peak_hbm, 'unit': 'GB/s',
+                         'frac': (hm_bytes / (decode_us * 1e-6) / 1e9) / peak_hbm if peak_hbm else None},
               'whole_step_tflops': GFLOP_PER_FRAME * B / ms_per_step}
 
   cpu = None

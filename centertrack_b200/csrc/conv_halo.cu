@@ -2,24 +2,29 @@
 // the im2row-free design for the thin, high-resolution layers (stems, level0, the 64-channel 128x128
 // layers, DCN offset convs, the fused head 3x3) where a per-tap gather is LSU-bound.
 //
-//   * Output tile = 8 (x) x 16 (y) pixels = 128 GEMM rows.  Its input neighbourhood (tile + halo) is
-//     fetched ONCE by TMA tensor copies (cp.async.bulk.tensor.4d, zero fill outside the image = the
-//     conv's zero padding) as C_in/8 un-swizzled "planes" [halo_y][halo_x][8 channels]: one pixel = one
-//     16-byte K-core row, 8 consecutive pixels = one 8x16B UMMA core matrix.
-//   * NO data is rearranged per tap: the A operand of tap (ky,kx) is the same shared-memory tile
-//     addressed through a UMMA descriptor whose start address is shifted by (ky*pitch + kx) pixels
-//     (K-major, SWIZZLE_NONE: LBO = plane stride (or 16 B = next pixel when C_in == 8, pairing two
-//     taps in one K=16 MMA), SBO = halo row pitch).
+//   * Output tile = 8 (x) x 16 (y) pixels = 128 GEMM rows (32 x 4 for 1x1 convs writing NCHW planes).  Its input
+//     neighbourhood (tile + halo) is fetched ONCE by TMA tensor copies (cp.async.bulk.tensor.4d, zero fill
+//     outside the image = the conv's zero padding).  Staging modes: whole-pixel K-major rows of 32/64/128 bytes
+//     with the matching hardware swizzle (C_in 16/32/64, and 64-channel chunks for C_in 128..256) -- one TMA
+//     request per pixel row; C_in == 8 (the packed stem input): 16-byte rows, two taps paired in one K=16 MMA;
+//     un-swizzled 8-channel "planes" [halo_y][halo_x][8] (debug: CTB_HALO_MODE=planes).
+//   * NO data is rearranged per tap: the A operand of tap (ky,kx) is the same shared-memory tile addressed
+//     through a UMMA descriptor whose start address is shifted by (ky*pitch + kx) pixel rows (the UMMA swizzle is
+//     a function of the shared-memory address, like the TMA's, so a shifted start needs no base-offset field);
+//     SBO = halo row pitch: the next 8-row core-matrix group is the next tile row.
 //   * Weights of one output-channel tile stay resident in shared memory for the CTA's lifetime
-//     (persistent CTAs, static tile striding); accumulators are double-buffered in TMEM so the
-//     epilogue of tile i overlaps the MMAs of tile i+1; halo tiles are double/triple buffered.
+//     (persistent CTAs, static tile striding); 2 or 4 accumulator stages in TMEM so the epilogue of tile i
+//     overlaps the MMAs of tile i+1 (and i+2); 2-4 halo stages.
 //
-// Warp roles (320 threads): warps 0-7 epilogue (warp w reads TMEM lanes 32(w%4)..; warps 0-3 take the even
-// 16-column chunks, 4-7 the odd ones -- the epilogue is instruction-latency bound, so two warps per SM
+// Warp roles (352 threads): warps 0-7 epilogue (warp w reads TMEM lanes 32(w%4)..; warps 0-3 take the even
+// 16-column chunks, 4-7 the odd ones -- the epilogue is an instruction-latency chain, so two warps per SM
 // sub-partition), warp 8 TMA producer, warps 9 and 10 MMA issuers (warp 9 also owns the TMEM allocation).
 // TWO issuing warps because one thread sustains only one tcgen05.mma per ~100 cycles on B200 whatever N is
 // (tools/mma_rate.cu: 91-115 cycles for N <= 128; two warps on separate accumulators reach 64.6 = the N=128 floor):
-// warp 9 takes the even work items / accumulator 0, warp 10 the odd items / accumulator 1.
+// warp 9 takes the even work items, warp 10 the odd ones; warp w owns accumulators w and w+2 and -- this matters --
+// the halo stages of its own parity (stage = item % S with S even): a stage's full-barrier must only ever be
+// waited on by ONE consumer warp, see the stage policy in conv_forward_halo().  Layers with few MMAs per item
+// (the 1x1 heads) run a single MMA warp and three stages instead.
 #include "conv_common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
