@@ -8,7 +8,6 @@ What differs underneath (`process`, detector.py:335-354): the network is a plan 
 launch, and the 7-13 per-key blocking D2H copies become one copy of the packed record buffer.
 Visualisation (`Debugger`, opt.debug >= 1) is outside the hot-path scope and is ignored.
 """
-import copy
 import math
 import time
 
@@ -22,6 +21,31 @@ from .model import create_model, load_model
 from .post_process import generic_post_process
 from .tracker import Tracker
 
+_STAGES = ('load', 'pre', 'net', 'dec', 'post', 'merge', 'track', 'display')
+
+
+class _StageClock(object):
+  """Wall-clock bookkeeping of `run` (the reference reports these eight stage totals plus `tot`)."""
+
+  def __init__(self):
+    self.t0 = self.mark = time.time()
+    self.acc = dict.fromkeys(_STAGES, 0.0)
+
+  def lap(self, stage, now=None):
+    now = time.time() if now is None else now
+    self.acc[stage] += now - self.mark
+    self.mark = now
+    return now
+
+  def report(self, results):
+    out = {'results': results, 'tot': self.mark - self.t0}
+    out.update(self.acc)
+    return out
+
+
+def _round_up(v, m):
+  return (v + m - 1) // m * m
+
 
 class Detector(object):
 
@@ -29,185 +53,167 @@ class Detector(object):
     if opt.gpus[0] < 0 or not torch.cuda.is_available():
       raise RuntimeError('centertrack_b200.Detector needs a CUDA device (B200, sm_100a); there is no '
                          'CPU fallback (got --gpus %s)' % getattr(opt, 'gpus_str', opt.gpus))
+    if opt.flip_test:
+      raise NotImplementedError('--flip_test is scheduled after the main path (SURVEY 8f-3)')
     opt.device = torch.device('cuda')
     print('Creating model...')
-    self.model = create_model(opt.arch, opt.heads, opt.head_conv, opt=opt)
-    if opt.load_model != '':
-      self.model = load_model(self.model, opt.load_model, opt)
+    model = create_model(opt.arch, opt.heads, opt.head_conv, opt=opt)
+    if opt.load_model:
+      model = load_model(model, opt.load_model, opt)
     else:
       print('Warning: no --load_model given; running with randomly initialised weights')
-    self.model = self.model.to(opt.device)
-    self.model.eval()
+    self.model = model.to(opt.device).eval()
     self.opt = opt
-    self.trained_dataset = get_dataset(opt.dataset)
-    self.mean = np.array(self.trained_dataset.mean, dtype=np.float32).reshape(1, 1, 3)
-    self.std = np.array(self.trained_dataset.std, dtype=np.float32).reshape(1, 1, 3)
+    ds = self.trained_dataset = get_dataset(opt.dataset)
+    self.mean = np.asarray(ds.mean, dtype=np.float32).reshape(1, 1, 3)
+    self.std = np.asarray(ds.std, dtype=np.float32).reshape(1, 1, 3)
+    self.rest_focal_length = opt.test_focal_length if opt.test_focal_length >= 0 else ds.rest_focal_length
+    self.flip_idx = ds.flip_idx
     self.pause = not opt.no_pause
-    self.rest_focal_length = self.trained_dataset.rest_focal_length \
-        if self.opt.test_focal_length < 0 else self.opt.test_focal_length
-    self.flip_idx = self.trained_dataset.flip_idx
     self.cnt = 0
     self.pre_images = None
     self.pre_image_ori = None
     self.tracker = Tracker(opt)
-    if opt.flip_test:
-      raise NotImplementedError('--flip_test is scheduled after the main path (SURVEY 8f-3)')
 
   # ------------------------------------------------------------------------------------ run
-  def run(self, image_or_path_or_tensor, meta={}):
-    load_time, pre_time, net_time, dec_time, post_time = 0, 0, 0, 0, 0
-    merge_time, track_time, tot_time, display_time = 0, 0, 0, 0
-    start_time = time.time()
-    pre_processed = False
-    if isinstance(image_or_path_or_tensor, np.ndarray):
-      image = image_or_path_or_tensor
-    elif type(image_or_path_or_tensor) == type(''):
+  def _open_input(self, source):
+    """ndarray (BGR HWC) | path | the dict test.py's DataLoader yields (already pre-processed per scale)."""
+    if isinstance(source, np.ndarray):
+      return source, None
+    if isinstance(source, str):
       import cv2
-      image = cv2.imread(image_or_path_or_tensor)
-    else:
-      image = image_or_path_or_tensor['image'][0].numpy()
-      pre_processed_images = image_or_path_or_tensor
-      pre_processed = True
-    loaded_time = time.time()
-    load_time += (loaded_time - start_time)
-    detections = []
+      return cv2.imread(source), None
+    return source['image'][0].numpy(), source
+
+  @staticmethod
+  def _scale_entry(packed, scale):
+    """(images, meta) of one test scale out of the DataLoader dict (detector.py:84-92)."""
+    meta = {k: v.numpy()[0] for k, v in packed['meta'][scale].items()}
+    for k in ('pre_dets', 'cur_dets'):
+      if k in packed['meta']:
+        meta[k] = packed['meta'][k]
+    return packed['images'][scale][0], meta
+
+  def _tracking_inputs(self, images, meta):
+    """First frame: the frame is its own pre_image and the tracker starts from `pre_dets`; then the prior heat-map
+    rendered from the live tracks (detector.py:97-110)."""
+    if not self.opt.tracking:
+      return None, None
+    if self.pre_images is None:
+      print('Initialize tracking!')
+      self.pre_images = images
+      self.tracker.init_track(meta.get('pre_dets', []))
+    if not self.opt.pre_hm:
+      return None, None
+    return self._get_additional_inputs(self.tracker.tracks, meta, with_hm=not self.opt.zero_pre_hm)
+
+  def run(self, image_or_path_or_tensor, meta={}):
+    """detector.py:55-172 without the visualisation branches; same return dict."""
+    clock = _StageClock()
+    image, packed = self._open_input(image_or_path_or_tensor)
+    clock.lap('load')
+    per_scale = []
     for scale in self.opt.test_scales:
-      scale_start_time = time.time()
-      if not pre_processed:
+      if packed is None:
         images, meta = self.pre_process(image, scale, meta)
       else:
-        images = pre_processed_images['images'][scale][0]
-        meta = pre_processed_images['meta'][scale]
-        meta = {k: v.numpy()[0] for k, v in meta.items()}
-        if 'pre_dets' in pre_processed_images['meta']:
-          meta['pre_dets'] = pre_processed_images['meta']['pre_dets']
-        if 'cur_dets' in pre_processed_images['meta']:
-          meta['cur_dets'] = pre_processed_images['meta']['cur_dets']
+        images, meta = self._scale_entry(packed, scale)
       images = images.to(self.opt.device, non_blocking=self.opt.non_block_test)
-      pre_hms, pre_inds = None, None
-      if self.opt.tracking:
-        if self.pre_images is None:
-          print('Initialize tracking!')
-          self.pre_images = images
-          self.tracker.init_track(meta['pre_dets'] if 'pre_dets' in meta else [])
-        if self.opt.pre_hm:
-          pre_hms, pre_inds = self._get_additional_inputs(
-              self.tracker.tracks, meta, with_hm=not self.opt.zero_pre_hm)
-      pre_process_time = time.time()
-      pre_time += pre_process_time - scale_start_time
-      output, dets, forward_time = self.process(images, self.pre_images, pre_hms, pre_inds,
-                                                return_time=True)
-      net_time += forward_time - pre_process_time
-      decode_time = time.time()
-      dec_time += decode_time - forward_time
-      result = self.post_process(dets, meta, scale)
-      post_process_time = time.time()
-      post_time += post_process_time - decode_time
-      detections.append(result)
-    results = self.merge_outputs(detections)
+      pre_hms, pre_inds = self._tracking_inputs(images, meta)
+      clock.lap('pre')
+      _, dets, t_forward = self.process(images, self.pre_images, pre_hms, pre_inds, return_time=True)
+      clock.lap('net', t_forward)
+      clock.lap('dec')
+      per_scale.append(self.post_process(dets, meta, scale))
+      clock.lap('post')
+    results = self.merge_outputs(per_scale)
     torch.cuda.synchronize()
-    end_time = time.time()
-    merge_time += end_time - post_process_time
+    t_merged = clock.lap('merge')
     if self.opt.tracking:
-      public_det = meta['cur_dets'] if self.opt.public_det else None
-      results = self.tracker.step(results, public_det)
+      results = self.tracker.step(results, meta['cur_dets'] if self.opt.public_det else None)
       self.pre_images = images
-    tracking_time = time.time()
-    track_time += tracking_time - end_time
-    tot_time += tracking_time - start_time
+    clock.lap('track')
     self.cnt += 1
-    display_time += time.time() - end_time
-    return {'results': results, 'tot': tot_time, 'load': load_time, 'pre': pre_time, 'net': net_time,
-            'dec': dec_time, 'post': post_time, 'merge': merge_time, 'track': track_time,
-            'display': display_time}
+    clock.acc['display'] += time.time() - t_merged        # the reference's display span starts at the merge mark
+    return clock.report(results)
 
   # ------------------------------------------------------------------------------------ host pre
-  def _transform_scale(self, image, scale=1):
-    """detector.py:175-204."""
-    import cv2
-    height, width = image.shape[0:2]
-    new_height, new_width = int(height * scale), int(width * scale)
-    if self.opt.fix_short > 0:
-      if height < width:
-        inp_height = self.opt.fix_short
-        inp_width = (int(width / height * self.opt.fix_short) + 63) // 64 * 64
-      else:
-        inp_height = (int(height / width * self.opt.fix_short) + 63) // 64 * 64
-        inp_width = self.opt.fix_short
-      c = np.array([width / 2, height / 2], dtype=np.float32)
-      s = np.array([width, height], dtype=np.float32)
-    elif self.opt.fix_res:
-      inp_height, inp_width = self.opt.input_h, self.opt.input_w
-      c = np.array([new_width / 2., new_height / 2.], dtype=np.float32)
-      s = max(height, width) * 1.0
+  def _input_geometry(self, height, width, scale):
+    """Network input size and the (centre, scale) of the source rectangle mapped onto it, for the three resolution
+    policies of detector.py:175-204: --fix_short (short side fixed, long side rounded up to 64), fixed resolution
+    (default), or keep_res (image size padded up to (size | pad) + 1)."""
+    opt = self.opt
+    sh, sw = int(height * scale), int(width * scale)
+    if opt.fix_short > 0:
+      long_side = lambda a, b: _round_up(int(a / b * opt.fix_short), 64)
+      inp_h, inp_w = (opt.fix_short, long_side(width, height)) if height < width else \
+                     (long_side(height, width), opt.fix_short)
+      centre = np.array([width / 2, height / 2], dtype=np.float32)
+      extent = np.array([width, height], dtype=np.float32)
+    elif opt.fix_res:
+      inp_h, inp_w = opt.input_h, opt.input_w
+      centre = np.array([sw / 2., sh / 2.], dtype=np.float32)
+      extent = max(height, width) * 1.0
     else:
-      inp_height = (new_height | self.opt.pad) + 1
-      inp_width = (new_width | self.opt.pad) + 1
-      c = np.array([new_width // 2, new_height // 2], dtype=np.float32)
-      s = np.array([inp_width, inp_height], dtype=np.float32)
-    resized_image = cv2.resize(image, (new_width, new_height))
-    return resized_image, c, s, inp_width, inp_height, height, width
+      inp_h, inp_w = (sh | opt.pad) + 1, (sw | opt.pad) + 1
+      centre = np.array([sw // 2, sh // 2], dtype=np.float32)
+      extent = np.array([inp_w, inp_h], dtype=np.float32)
+    return (sh, sw), centre, extent, inp_w, inp_h
+
+  def _transform_scale(self, image, scale=1):
+    """Reference-named helper (detector.py:175): resized image + geometry tuple."""
+    import cv2
+    height, width = image.shape[:2]
+    (sh, sw), c, s, inp_w, inp_h = self._input_geometry(height, width, scale)
+    return cv2.resize(image, (sw, sh)), c, s, inp_w, inp_h, height, width
 
   def pre_process(self, image, scale, input_meta={}):
     """detector.py:207-239 (CPU only and fork-safe: test.py hands it to a DataLoader worker).
-    Like the reference (hazard H5) `scale` is not forwarded to _transform_scale."""
+    Like the reference (hazard H5) `scale` is not forwarded to the geometry."""
     import cv2
-    resized_image, c, s, inp_width, inp_height, height, width = self._transform_scale(image)
-    trans_input = get_affine_transform(c, s, 0, [inp_width, inp_height])
-    out_height = inp_height // self.opt.down_ratio
-    out_width = inp_width // self.opt.down_ratio
-    trans_output = get_affine_transform(c, s, 0, [out_width, out_height])
-    inp_image = cv2.warpAffine(resized_image, trans_input, (inp_width, inp_height), flags=cv2.INTER_LINEAR)
-    inp_image = ((inp_image / 255. - self.mean) / self.std).astype(np.float32)
-    images = inp_image.transpose(2, 0, 1).reshape(1, 3, inp_height, inp_width)
-    images = torch.from_numpy(images)
-    meta = {'calib': np.array(input_meta['calib'], dtype=np.float32) if 'calib' in input_meta
-            else self._get_default_calib(width, height)}
-    meta.update({'c': c, 's': s, 'height': height, 'width': width, 'out_height': out_height,
-                 'out_width': out_width, 'inp_height': inp_height, 'inp_width': inp_width,
-                 'trans_input': trans_input, 'trans_output': trans_output})
-    if 'pre_dets' in input_meta:
-      meta['pre_dets'] = input_meta['pre_dets']
-    if 'cur_dets' in input_meta:
-      meta['cur_dets'] = input_meta['cur_dets']
+    resized, c, s, inp_w, inp_h, height, width = self._transform_scale(image)
+    out_w, out_h = inp_w // self.opt.down_ratio, inp_h // self.opt.down_ratio
+    to_input = get_affine_transform(c, s, 0, [inp_w, inp_h])
+    to_output = get_affine_transform(c, s, 0, [out_w, out_h])
+    warped = cv2.warpAffine(resized, to_input, (inp_w, inp_h), flags=cv2.INTER_LINEAR)
+    chw = ((warped / 255. - self.mean) / self.std).astype(np.float32).transpose(2, 0, 1)
+    images = torch.from_numpy(chw.reshape(1, 3, inp_h, inp_w))
+    calib = np.array(input_meta['calib'], dtype=np.float32) if 'calib' in input_meta \
+        else self._get_default_calib(width, height)
+    meta = dict(calib=calib, c=c, s=s, height=height, width=width, out_height=out_h, out_width=out_w,
+                inp_height=inp_h, inp_width=inp_w, trans_input=to_input, trans_output=to_output)
+    meta.update({k: input_meta[k] for k in ('pre_dets', 'cur_dets') if k in input_meta})
     return images, meta
 
   def _trans_bbox(self, bbox, trans, width, height):
-    bbox = np.array(copy.deepcopy(bbox), dtype=np.float32)
-    bbox[:2] = affine_transform(bbox[:2], trans)
-    bbox[2:] = affine_transform(bbox[2:], trans)
-    bbox[[0, 2]] = np.clip(bbox[[0, 2]], 0, width - 1)
-    bbox[[1, 3]] = np.clip(bbox[[1, 3]], 0, height - 1)
-    return bbox
+    """Box corners through a 2x3 affine map, clipped to [0, width-1] x [0, height-1] (detector.py:242-251)."""
+    corners = np.asarray(bbox, dtype=np.float32).reshape(2, 2)
+    moved = np.stack([affine_transform(corners[0], trans), affine_transform(corners[1], trans)]).astype(np.float32)
+    return np.clip(moved, 0, np.array([width - 1, height - 1], dtype=np.float32)).reshape(4)
 
   def _get_additional_inputs(self, dets, meta, with_hm=True):
-    """detector.py:254-290: render pre_hm at input resolution from the active tracks."""
-    trans_input, trans_output = meta['trans_input'], meta['trans_output']
-    inp_width, inp_height = meta['inp_width'], meta['inp_height']
-    out_width, out_height = meta['out_width'], meta['out_height']
-    input_hm = np.zeros((1, inp_height, inp_width), dtype=np.float32)
-    output_inds = []
-    for det in dets:
-      if det['score'] < self.opt.pre_thresh or det['active'] == 0:
+    """detector.py:254-290: the prior heat-map [1,1,inp_h,inp_w] splatted from the tracks that are active and score at
+    least pre_thresh, plus their centre indices on the output grid."""
+    inp_w, inp_h, out_w, out_h = meta['inp_width'], meta['inp_height'], meta['out_width'], meta['out_height']
+    canvas = np.zeros((1, inp_h, inp_w), dtype=np.float32)
+    inds = []
+    for trk in dets:
+      if trk['active'] == 0 or trk['score'] < self.opt.pre_thresh:
         continue
-      bbox = self._trans_bbox(det['bbox'], trans_input, inp_width, inp_height)
-      bbox_out = self._trans_bbox(det['bbox'], trans_output, out_width, out_height)
-      h, w = bbox[3] - bbox[1], bbox[2] - bbox[0]
-      if h > 0 and w > 0:
-        radius = gaussian_radius((math.ceil(h), math.ceil(w)))
-        radius = max(0, int(radius))
-        ct = np.array([(bbox[0] + bbox[2]) / 2, (bbox[1] + bbox[3]) / 2], dtype=np.float32)
-        ct_int = ct.astype(np.int32)
-        if with_hm:
-          draw_umich_gaussian(input_hm[0], ct_int, radius)
-        ct_out = np.array([(bbox_out[0] + bbox_out[2]) / 2, (bbox_out[1] + bbox_out[3]) / 2],
-                          dtype=np.int32)
-        output_inds.append(ct_out[1] * out_width + ct_out[0])
+      x0, y0, x1, y1 = self._trans_bbox(trk['bbox'], meta['trans_input'], inp_w, inp_h)
+      if not (y1 - y0 > 0 and x1 - x0 > 0):
+        continue
+      if with_hm:
+        radius = max(0, int(gaussian_radius((math.ceil(y1 - y0), math.ceil(x1 - x0)))))
+        centre = np.array([(x0 + x1) / 2, (y0 + y1) / 2], dtype=np.float32)
+        draw_umich_gaussian(canvas[0], centre.astype(np.int32), radius)
+      ox0, oy0, ox1, oy1 = self._trans_bbox(trk['bbox'], meta['trans_output'], out_w, out_h)
+      cell = np.array([(ox0 + ox1) / 2, (oy0 + oy1) / 2], dtype=np.int32)
+      inds.append(cell[1] * out_w + cell[0])
     if with_hm:
-      input_hm = torch.from_numpy(input_hm[np.newaxis]).to(self.opt.device)
-    output_inds = np.array(output_inds, np.int64).reshape(1, -1)
-    output_inds = torch.from_numpy(output_inds).to(self.opt.device)
-    return input_hm, output_inds
+      canvas = torch.from_numpy(canvas[np.newaxis]).to(self.opt.device)
+    pre_inds = torch.from_numpy(np.array(inds, np.int64).reshape(1, -1)).to(self.opt.device)
+    return canvas, pre_inds
 
   def _get_default_calib(self, width, height):
     return np.array([[self.rest_focal_length, 0, width / 2, 0],

@@ -156,10 +156,61 @@ def gen_post_track():
   print('post_track', len(data), 'arrays')
 
 
+HOST_CASES = [  # (name, extra opts argv, image (h, w), input_meta has calib)
+    ('fix_res', ['--input_h', '128', '--input_w', '160'], (120, 200), False),
+    ('fix_res_tall', ['--input_h', '160', '--input_w', '128'], (333, 210), True),
+    ('keep_res', ['--keep_res'], (97, 131), False),
+    ('fix_short', ['--fix_short', '96'], (150, 260), False),
+    ('fix_short_tall', ['--fix_short', '64'], (300, 170), True)]
+
+
+def host_case_inputs(i, hw):
+  rng = np.random.RandomState(900 + i)
+  image = rng.randint(0, 256, size=(hw[0], hw[1], 3)).astype(np.uint8)
+  n = 6
+  x0 = rng.uniform(-10, hw[1] * 0.8, n); y0 = rng.uniform(-10, hw[0] * 0.8, n)
+  w = rng.uniform(0, hw[1] * 0.5, n); h = rng.uniform(0, hw[0] * 0.5, n)
+  w[0] = 0.0                                              # degenerate box: skipped by the reference
+  tracks = [{'score': float(sc), 'active': int(ac), 'bbox': [float(a), float(b), float(a + c), float(b + d)]}
+            for sc, ac, a, b, c, d in zip(rng.uniform(0.1, 1.0, n), [1, 1, 0, 1, 1, 1], x0, y0, w, h)]
+  tracks[3]['score'] = 0.05                               # below pre_thresh
+  calib = np.array([[700., 0, hw[1] / 2., 40.], [0, 700., hw[0] / 2., 1.], [0, 0, 1, 0.01]], dtype=np.float32)
+  return image, tracks, calib
+
+
+def gen_host():
+  """Detector.pre_process / _get_additional_inputs of the reference (detector.py:175-290), model-free: the
+  methods are called on an instance built without __init__ (no checkpoint, no device)."""
+  from detector import Detector as RefDetector
+  from dataset.dataset_factory import get_dataset
+  data = {}
+  for i, (name, extra, hw, with_calib) in enumerate(HOST_CASES):
+    opt = rh.make_opt('coco_tracking', extra=['--pre_thresh', '0.3'] + extra)
+    det = object.__new__(RefDetector)
+    ds = get_dataset(opt.dataset)
+    opt.device = torch.device('cpu')                        # set by Detector.__init__ in the reference
+    det.opt = opt
+    det.mean = np.array(ds.mean, dtype=np.float32).reshape(1, 1, 3)
+    det.std = np.array(ds.std, dtype=np.float32).reshape(1, 1, 3)
+    det.rest_focal_length = ds.rest_focal_length
+    image, tracks, calib = host_case_inputs(i, hw)
+    images, meta = det.pre_process(image, 1.0, {'calib': calib} if with_calib else {})
+    data[name + '.images'] = images.numpy()
+    for k in ('c', 's', 'calib', 'trans_input', 'trans_output'):
+      data[name + '.meta.' + k] = np.asarray(meta[k], dtype=np.float64)
+    data[name + '.meta.ints'] = np.array([meta[k] for k in ('height', 'width', 'out_height', 'out_width',
+                                                             'inp_height', 'inp_width')], dtype=np.int64)
+    hm, inds = det._get_additional_inputs(tracks, meta, with_hm=True)
+    data[name + '.pre_hm'] = hm.numpy()
+    data[name + '.pre_inds'] = inds.numpy()
+  np.savez_compressed(os.path.join(OUT, 'host_pre.npz'), **data)
+  print('host_pre', len(data), 'arrays')
+
+
 if __name__ == '__main__':
   os.makedirs(OUT, exist_ok=True)
   torch.manual_seed(0)
-  which = sys.argv[1:] or ['net', 'e2e', 'decode', 'post']
+  which = sys.argv[1:] or ['net', 'e2e', 'decode', 'post', 'host']
   rh.install()
   if 'net' in which:
     gen_net()
@@ -169,3 +220,5 @@ if __name__ == '__main__':
     gen_post_track()
   if 'e2e' in which:
     gen_e2e()
+  if 'host' in which:
+    gen_host()

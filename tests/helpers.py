@@ -56,3 +56,25 @@ def decode_inputs(kind, B, C, H, W, seed):
 DECODE_CASES = [('coco', 1, 80, 128, 128, 100, 11), ('mot', 1, 1, 136, 240, 100, 12),
                 ('ddd', 1, 10, 112, 200, 100, 13), ('pose', 1, 1, 128, 128, 100, 14),
                 ('coco', 2, 80, 32, 32, 50, 15)]
+
+
+# Must stay identical to oracle/gen_golden.py::HOST_CASES / host_case_inputs (Detector.pre_process goldens).
+HOST_CASES = [('fix_res', ['--input_h', '128', '--input_w', '160'], (120, 200), False),
+              ('fix_res_tall', ['--input_h', '160', '--input_w', '128'], (333, 210), True),
+              ('keep_res', ['--keep_res'], (97, 131), False),
+              ('fix_short', ['--fix_short', '96'], (150, 260), False),
+              ('fix_short_tall', ['--fix_short', '64'], (300, 170), True)]
+
+
+def host_case_inputs(i, hw):
+  rng = np.random.RandomState(900 + i)
+  image = rng.randint(0, 256, size=(hw[0], hw[1], 3)).astype(np.uint8)
+  n = 6
+  x0 = rng.uniform(-10, hw[1] * 0.8, n); y0 = rng.uniform(-10, hw[0] * 0.8, n)
+  w = rng.uniform(0, hw[1] * 0.5, n); h = rng.uniform(0, hw[0] * 0.5, n)
+  w[0] = 0.0
+  tracks = [{'score': float(sc), 'active': int(ac), 'bbox': [float(a), float(b), float(a + c), float(b + d)]}
+            for sc, ac, a, b, c, d in zip(rng.uniform(0.1, 1.0, n), [1, 1, 0, 1, 1, 1], x0, y0, w, h)]
+  tracks[3]['score'] = 0.05
+  calib = np.array([[700., 0, hw[1] / 2., 40.], [0, 700., hw[0] / 2., 1.], [0, 0, 1, 0.01]], dtype=np.float32)
+  return image, tracks, calib

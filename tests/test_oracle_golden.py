@@ -12,7 +12,7 @@ import torch
 
 import ct_oracle as co
 from centertrack_b200 import synthetic as wt
-from helpers import DECODE_CASES, decode_inputs, make_opt, make_model
+from helpers import DECODE_CASES, HOST_CASES, decode_inputs, host_case_inputs, make_opt, make_model
 
 
 @pytest.mark.parametrize('cfg', ['coco_tracking', 'mot', 'nuscenes_ddd', 'coco_pose'])
@@ -134,3 +134,36 @@ def test_oracle_topk_tie_rule():
   v = np.array([[0.5, 0.0, 0.5, 0.7, 0.0, 0.0]], dtype=np.float32)
   s, i = co.topk_desc(v, 4)
   assert list(i[0]) == [3, 0, 2, 1] and list(s[0]) == [0.7, 0.5, 0.5, 0.0]
+
+
+@pytest.mark.parametrize('i', range(len(HOST_CASES)), ids=[c[0] for c in HOST_CASES])
+def test_product_host_pre_process_and_pre_hm_match_reference_golden(i, golden_dir):
+  """Detector.pre_process / _transform_scale / _get_additional_inputs (host numpy + cv2; rows a17, a18) against the
+  unmodified reference's outputs: every resolution mode (fix_res, keep_res, fix_short), calib given or default,
+  tracks that are inactive / below pre_thresh / degenerate / partly outside the image."""
+  from centertrack_b200.detector import Detector
+  from centertrack_b200.dataset_info import get_dataset
+  g = np.load(os.path.join(golden_dir, 'host_pre.npz'))
+  name, extra, hw, with_calib = HOST_CASES[i]
+  opt = make_opt('coco_tracking', ['--pre_thresh', '0.3'] + extra)
+  opt.device = torch.device('cpu')
+  det = object.__new__(Detector)              # host methods only: no model, no device
+  ds = get_dataset(opt.dataset)
+  det.opt = opt
+  det.mean = np.array(ds.mean, dtype=np.float32).reshape(1, 1, 3)
+  det.std = np.array(ds.std, dtype=np.float32).reshape(1, 1, 3)
+  det.rest_focal_length = ds.rest_focal_length
+  image, tracks, calib = host_case_inputs(i, hw)
+  images, meta = det.pre_process(image, 1.0, {'calib': calib} if with_calib else {})
+  # the affine matrices come from a closed-form solve here and from cv2.getAffineTransform in the reference:
+  # equal to ~1e-16; the warped image may differ by an interpolation rounding on isolated pixels
+  assert images.dtype == torch.float32 and images.shape == g[name + '.images'].shape
+  err = np.abs(images.numpy() - g[name + '.images'])
+  assert err.max() <= 2e-2 and (err > 1e-5).mean() < 1e-3, (err.max(), (err > 1e-5).mean())
+  for k in ('c', 's', 'calib', 'trans_input', 'trans_output'):
+    assert np.allclose(np.asarray(meta[k], dtype=np.float64), g[name + '.meta.' + k], rtol=0, atol=1e-9), k
+  ints = [meta[k] for k in ('height', 'width', 'out_height', 'out_width', 'inp_height', 'inp_width')]
+  assert np.array_equal(np.array(ints, dtype=np.int64), g[name + '.meta.ints'])
+  hm, inds = det._get_additional_inputs(tracks, meta, with_hm=True)
+  assert tuple(hm.shape) == g[name + '.pre_hm'].shape and np.array_equal(hm.numpy(), g[name + '.pre_hm'])
+  assert inds.dtype == torch.int64 and np.array_equal(inds.numpy(), g[name + '.pre_inds'])
