@@ -93,33 +93,27 @@ class opts(object):
     return opt
 
   def update_dataset_info_and_set_heads(self, opt, dataset):
-    opt.num_classes = dataset.num_categories if opt.num_classes < 0 else opt.num_classes
-    input_h, input_w = dataset.default_resolution
-    input_h = opt.input_res if opt.input_res > 0 else input_h
-    input_w = opt.input_res if opt.input_res > 0 else input_w
-    opt.input_h = opt.input_h if opt.input_h > 0 else input_h
-    opt.input_w = opt.input_w if opt.input_w > 0 else input_w
-    opt.output_h = opt.input_h // opt.down_ratio
-    opt.output_w = opt.input_w // opt.down_ratio
-    opt.input_res = max(opt.input_h, opt.input_w)
-    opt.output_res = max(opt.output_h, opt.output_w)
-    opt.heads = {'hm': opt.num_classes, 'reg': 2, 'wh': 2}
-    if 'tracking' in opt.task:
-      opt.heads.update({'tracking': 2})
-    if 'ddd' in opt.task:
-      opt.heads.update({'dep': 1, 'rot': 8, 'dim': 3, 'amodel_offset': 2})
-    if 'multi_pose' in opt.task:
-      opt.heads.update({'hps': dataset.num_joints * 2, 'hm_hp': dataset.num_joints, 'hp_offset': 2})
-    if opt.ltrb:
-      opt.heads.update({'ltrb': 4})
-    if opt.ltrb_amodal:
-      opt.heads.update({'ltrb_amodal': 4})
-    if opt.nuscenes_att:
-      opt.heads.update({'nuscenes_att': 8})
-    if opt.velocity:
-      opt.heads.update({'velocity': 3})
-    opt.head_conv = {head: [opt.head_conv for _ in range(opt.num_head_conv if head != 'reg' else 1)]
-                     for head in opt.heads}
+    """opts.py:322-388 of the reference: resolution defaults from the dataset, then the head table
+    {name: channels} in the reference's insertion order (the state-dict and the decode roles depend on it)."""
+    if opt.num_classes < 0:
+      opt.num_classes = dataset.num_categories
+    default_h, default_w = (opt.input_res, opt.input_res) if opt.input_res > 0 else dataset.default_resolution
+    if opt.input_h <= 0:
+      opt.input_h = default_h
+    if opt.input_w <= 0:
+      opt.input_w = default_w
+    opt.output_h, opt.output_w = opt.input_h // opt.down_ratio, opt.input_w // opt.down_ratio
+    opt.input_res, opt.output_res = max(opt.input_h, opt.input_w), max(opt.output_h, opt.output_w)
+    joints = getattr(dataset, 'num_joints', 0)
+    head_table = [(True, (('hm', opt.num_classes), ('reg', 2), ('wh', 2))),
+                  ('tracking' in opt.task, (('tracking', 2),)),
+                  ('ddd' in opt.task, (('dep', 1), ('rot', 8), ('dim', 3), ('amodel_offset', 2))),
+                  ('multi_pose' in opt.task, (('hps', 2 * joints), ('hm_hp', joints), ('hp_offset', 2))),
+                  (opt.ltrb, (('ltrb', 4),)), (opt.ltrb_amodal, (('ltrb_amodal', 4),)),
+                  (opt.nuscenes_att, (('nuscenes_att', 8),)), (opt.velocity, (('velocity', 3),))]
+    opt.heads = {name: ch for enabled, group in head_table if enabled for name, ch in group}
+    width = opt.head_conv
+    opt.head_conv = {name: [width] * (1 if name == 'reg' else opt.num_head_conv) for name in opt.heads}
     return opt
 
   def init(self, args=''):
