@@ -167,3 +167,56 @@ def test_product_host_pre_process_and_pre_hm_match_reference_golden(i, golden_di
   hm, inds = det._get_additional_inputs(tracks, meta, with_hm=True)
   assert tuple(hm.shape) == g[name + '.pre_hm'].shape and np.array_equal(hm.numpy(), g[name + '.pre_hm'])
   assert inds.dtype == torch.int64 and np.array_equal(inds.numpy(), g[name + '.pre_inds'])
+
+
+def test_detector_run_host_control_flow_with_stubbed_device_path(monkeypatch):
+  """Detector.run's host orchestration (input kinds, first-frame tracker initialisation, pre_hm render, post_process,
+  tracker step, the reference's return dict) with `process` -- the only method that touches the GPU -- replaced by a
+  stub that decodes synthetic maps with the oracle.  Compared step by step with the same pipeline assembled by hand."""
+  import time
+  from centertrack_b200.detector import Detector
+  from centertrack_b200.dataset_info import get_dataset
+  from centertrack_b200.tracker import Tracker
+  opt = make_opt('coco_tracking', ['--input_h', '128', '--input_w', '160', '--track_thresh', '0.05',
+                                   '--new_thresh', '0.05', '--pre_thresh', '0.05'])
+  opt.device = torch.device('cpu')
+  det = object.__new__(Detector)
+  ds = get_dataset(opt.dataset)
+  det.opt, det.cnt, det.pre_images, det.tracker = opt, 0, None, Tracker(opt)
+  det.mean = np.array(ds.mean, dtype=np.float32).reshape(1, 1, 3)
+  det.std = np.array(ds.std, dtype=np.float32).reshape(1, 1, 3)
+  det.rest_focal_length = ds.rest_focal_length
+  monkeypatch.setattr(torch.cuda, 'synchronize', lambda *a, **k: None)
+  seen = []
+
+  def fake_process(images, pre_images=None, pre_hms=None, pre_inds=None, return_time=False):
+    seen.append((tuple(images.shape), pre_images is not None, None if pre_hms is None else float(pre_hms.max()),
+                 None if pre_inds is None else int(pre_inds.numel())))
+    maps = decode_inputs('coco', 1, 80, 32, 40, 500 + len(seen))
+    dets = {k: v for k, v in co.generic_decode(maps, 100).items() if not k.startswith('_')}
+    return {}, dets, time.time()
+
+  det.process = fake_process
+  rng = np.random.RandomState(5)
+  ref_tracker = Tracker(opt)
+  ref_tracker.init_track([])
+  for f in range(3):
+    frame = rng.randint(0, 255, (120, 160, 3)).astype(np.uint8)
+    ret = det.run(frame)
+    assert set(ret) == {'results', 'tot', 'load', 'pre', 'net', 'dec', 'post', 'merge', 'track', 'display'}
+    assert all(ret[k] >= 0 for k in ret if k != 'results') and ret['tot'] >= ret['net']
+    # the same step by hand
+    _, meta = det.pre_process(frame, 1.0)
+    maps = decode_inputs('coco', 1, 80, 32, 40, 500 + f + 1)
+    dets = {k: v for k, v in co.generic_decode(maps, 100).items() if not k.startswith('_')}
+    want = ref_tracker.step(det.merge_outputs([det.post_process(dets, meta, 1.0)]))
+    got = ret['results']
+    assert len(got) == len(want) > 0
+    for a, b in zip(got, want):
+      assert a['tracking_id'] == b['tracking_id'] and a['class'] == b['class'] and a['active'] == b['active']
+      assert np.array_equal(np.asarray(a['bbox']), np.asarray(b['bbox']))
+    # device-path arguments: first frame is its own pre_image; pre_hm is empty until tracks exist
+    shape, has_pre, hm_max, n_inds = seen[f]
+    assert shape == (1, 3, 128, 160) and has_pre
+    assert (hm_max == 0.0 and n_inds == 0) if f == 0 else (hm_max > 0.5 and n_inds > 0)
+  assert det.cnt == 3 and det.tracker.id_count == ref_tracker.id_count
