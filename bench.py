@@ -93,6 +93,7 @@ def run_reference(args, rank, world):
   reference itself cannot travel to the GPU box) on all host threads.  Rank 0 only."""
   if rank != 0:
     return
+  torch.set_num_threads(os.cpu_count() or 1)       # torchrun exports OMP_NUM_THREADS=1; this arm owns the host
   frames_per_step = 1
   for _ in range(min(args.warmup, 1)):
     _oracle_step(1)
@@ -309,7 +310,8 @@ def main():
               'whole_step_tflops': GFLOP_PER_FRAME * B / ms_per_step}
 
   cpu = None
-  if not args.no_cpu_baseline:
+  if not args.no_cpu_baseline and world == 1:       # rank 0 at N=1 only; all host threads
+    torch.set_num_threads(os.cpu_count() or 1)
     _oracle_step(1)                                     # warm-up (oneDNN primitive caches)
     n = 3
     dt, thr = _oracle_step(n)
