@@ -178,6 +178,42 @@ def host_case_inputs(i, hw):
   return image, tracks, calib
 
 
+OPT_CASES = [['tracking'], ['tracking', '--pre_hm', '--track_thresh', '0.4', '--pre_thresh', '0.5'],
+             ['tracking', '--num_classes', '1', '--input_h', '544', '--input_w', '960', '--ltrb_amodal', '--pre_hm'],
+             ['tracking,ddd', '--pre_hm', '--nuscenes_att', '--velocity', '--input_res', '640'],
+             ['tracking,multi_pose', '--keep_res', '--K', '50', '--num_head_conv', '2'],
+             ['ctdet', '--head_conv', '128', '--test_scales', '1', '--fix_short', '512', '--out_thresh', '0.2'],
+             ['tracking', '--no_pre_img', '--zero_pre_hm', '--zero_tracking', '--max_age', '3', '--new_thresh', '0.6']]
+OPT_FIELDS = ['task', 'dataset', 'test_dataset', 'arch', 'heads', 'head_conv', 'num_classes', 'input_h', 'input_w',
+              'output_h', 'output_w', 'input_res', 'output_res', 'down_ratio', 'pad', 'num_stacks', 'fix_res', 'fix_short',
+              'tracking', 'pre_img', 'pre_hm', 'zero_pre_hm', 'zero_tracking', 'out_thresh', 'pre_thresh', 'new_thresh',
+              'track_thresh', 'max_age', 'K', 'test_scales', 'head_kernel', 'prior_bias', 'ltrb', 'ltrb_amodal',
+              'nuscenes_att', 'velocity', 'depth_scale', 'flip_test', 'public_det', 'hungarian', 'model_output_list']
+
+
+def gen_opts():
+  """Derived option fields of the reference's opts().init() (opts.py:257-403) for a set of command lines."""
+  import io, contextlib, json
+  from opts import opts
+  out = []
+  for argv in OPT_CASES:
+    old = sys.argv
+    sys.argv = ['demo.py'] + argv + ['--gpus', '-1']
+    try:
+      with contextlib.redirect_stdout(io.StringIO()):
+        opt = opts().init()
+    finally:
+      sys.argv = old
+    rec = {}
+    for k in OPT_FIELDS:
+      v = getattr(opt, k)
+      rec[k] = [[n, c] for n, c in v.items()] if isinstance(v, dict) else v      # dicts keep their insertion order
+    out.append(rec)
+  with open(os.path.join(OUT, 'opts_cases.json'), 'w') as f:
+    json.dump({'cases': OPT_CASES, 'fields': out}, f, indent=1)
+  print('opts', len(out), 'cases')
+
+
 def gen_host():
   """Detector.pre_process / _get_additional_inputs of the reference (detector.py:175-290), model-free: the
   methods are called on an instance built without __init__ (no checkpoint, no device)."""
@@ -210,7 +246,7 @@ def gen_host():
 if __name__ == '__main__':
   os.makedirs(OUT, exist_ok=True)
   torch.manual_seed(0)
-  which = sys.argv[1:] or ['net', 'e2e', 'decode', 'post', 'host']
+  which = sys.argv[1:] or ['net', 'e2e', 'decode', 'post', 'host', 'opts']
   rh.install()
   if 'net' in which:
     gen_net()
@@ -222,3 +258,5 @@ if __name__ == '__main__':
     gen_e2e()
   if 'host' in which:
     gen_host()
+  if 'opts' in which:
+    gen_opts()

@@ -220,3 +220,51 @@ def test_detector_run_host_control_flow_with_stubbed_device_path(monkeypatch):
     assert shape == (1, 3, 128, 160) and has_pre
     assert (hm_max == 0.0 and n_inds == 0) if f == 0 else (hm_max > 0.5 and n_inds > 0)
   assert det.cnt == 3 and det.tracker.id_count == ref_tracker.id_count
+
+
+def test_product_opts_derive_the_same_fields_as_the_reference(golden_dir):
+  """centertrack_b200.opts vs the reference's opts().init() on seven command lines (tests/golden/opts_cases.json):
+  heads (names, channels AND order), head_conv, resolutions, thresholds, tracking switches."""
+  import json
+  from centertrack_b200.opts import opts
+  g = json.load(open(os.path.join(golden_dir, 'opts_cases.json')))
+  for argv, want in zip(g['cases'], g['fields']):
+    opt = opts().init(argv + ['--gpus', '-1'])
+    for k, v in want.items():
+      got = getattr(opt, k)
+      if isinstance(got, dict):
+        got = [[n, c] for n, c in got.items()]
+      assert got == v, (argv, k, got, v)
+
+
+@pytest.mark.parametrize('seed', range(8))
+def test_product_tracker_equals_oracle_on_random_streams(seed):
+  """Randomised streams (crowded scenes, class changes, empty frames, tracks that coast with --max_age) through
+  centertrack_b200.tracker.Tracker and the oracle restatement (itself pinned to the reference by post_track.npz)."""
+  import copy
+  from centertrack_b200.tracker import Tracker
+  rng = np.random.RandomState(seed)
+  max_age = [-1, 2][seed % 2]
+  opt = make_opt('coco_tracking', ['--track_thresh', '0.2', '--new_thresh', '0.3', '--max_age', str(max_age)])
+  prod, orc = Tracker(opt), co.TrackerOracle(opt.new_thresh, max_age)
+  first = True
+  for frame in range(6):
+    n = 0 if (seed == 3 and frame == 2) else int(rng.randint(1, 40))
+    dets = []
+    for _ in range(n):
+      ct = rng.uniform(0, 200, 2)
+      wh = rng.uniform(2, 60, 2)
+      dets.append({'score': float(rng.uniform(0.2, 1.0)), 'class': int(rng.randint(1, 4)),
+                   'ct': ct.astype(np.float32), 'tracking': rng.normal(0, 6, 2).astype(np.float32),
+                   'bbox': np.array([ct[0] - wh[0] / 2, ct[1] - wh[1] / 2, ct[0] + wh[0] / 2, ct[1] + wh[1] / 2],
+                                    np.float32)})
+    dets.sort(key=lambda d: -d['score'])
+    a, b = copy.deepcopy(dets), copy.deepcopy(dets)
+    if first:
+      prod.init_track([]); orc.init_track([])
+      first = False
+    ra, rb = prod.step(a), orc.step(b)
+    assert len(ra) == len(rb) and prod.id_count == orc.id_count
+    for x, y in zip(ra, rb):
+      assert (x['tracking_id'], x['age'], x['active'], x['class']) == (y['tracking_id'], y['age'], y['active'], y['class'])
+      assert np.array_equal(x['bbox'], y['bbox'])
