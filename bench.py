@@ -313,7 +313,7 @@ def main():
   if not args.no_cpu_baseline and world == 1:       # rank 0 at N=1 only; all host threads
     torch.set_num_threads(os.cpu_count() or 1)
     _oracle_step(1)                                     # warm-up (oneDNN primitive caches)
-    n = 3
+    n = 10                                              # ~10 s of wall clock on the box's 64 host threads
     dt, thr = _oracle_step(n)
     cpu = {'value': n / dt, 'unit': 'frames/s', 'cores': thr, 'kind': 'port',
            'sample': '%d frames 512x512 (oracle/ct_oracle.py, torch-CPU fp32)' % n}
