@@ -70,6 +70,17 @@ class ClockSampler(threading.Thread):
             'reasons': sorted(reasons), 'samples': len(self.rows)}
 
 
+def _use_host_threads():
+  """torch's own default thread count is kept (64 on the GPU box: oversubscribing its logical CPUs made the oracle
+  several times slower); only when a launcher pinned it to one thread (torchrun exports OMP_NUM_THREADS=1) is it
+  raised, to half the logical CPUs (= physical cores on an SMT-2 host).  CTB_CPU_THREADS overrides."""
+  n = int(os.environ.get('CTB_CPU_THREADS', '0'))
+  if n <= 0 and torch.get_num_threads() <= 1:
+    n = max(1, (os.cpu_count() or 2) // 2)
+  if n > 0:
+    torch.set_num_threads(n)
+
+
 def _oracle_step(n_frames=1):
   """The CPU restatement of the reference path (oracle/), timed on this host: network + sigmoid +
   decode for n_frames 512x512 frame pairs.  Returns (seconds, threads)."""
@@ -93,7 +104,7 @@ def run_reference(args, rank, world):
   reference itself cannot travel to the GPU box) on all host threads.  Rank 0 only."""
   if rank != 0:
     return
-  torch.set_num_threads(os.cpu_count() or 1)       # torchrun exports OMP_NUM_THREADS=1; this arm owns the host
+  _use_host_threads()
   frames_per_step = 1
   for _ in range(min(args.warmup, 1)):
     _oracle_step(1)
@@ -310,8 +321,8 @@ def main():
               'whole_step_tflops': GFLOP_PER_FRAME * B / ms_per_step}
 
   cpu = None
-  if not args.no_cpu_baseline and world == 1:       # rank 0 at N=1 only; all host threads
-    torch.set_num_threads(os.cpu_count() or 1)
+  if not args.no_cpu_baseline and world == 1:       # rank 0 at N=1 only
+    _use_host_threads()
     _oracle_step(1)                                     # warm-up (oneDNN primitive caches)
     n = 10                                              # ~10 s of wall clock on the box's 64 host threads
     dt, thr = _oracle_step(n)
