@@ -81,9 +81,10 @@ def _use_host_threads():
     torch.set_num_threads(n)
 
 
-def _oracle_step(n_frames=1):
+def _oracle_step(n_frames=1, budget_s=None):
   """The CPU restatement of the reference path (oracle/), timed on this host: network + sigmoid +
-  decode for n_frames 512x512 frame pairs.  Returns (seconds, threads)."""
+  decode for up to n_frames 512x512 frame pairs (stops early once budget_s seconds have elapsed, so a slow or
+  oversubscribed host cannot stall the bench).  Returns (seconds, threads, frames done)."""
   sys.path.insert(0, os.path.join(ROOT, 'oracle'))
   sys.path.insert(0, os.path.join(ROOT, 'tests'))
   import ct_oracle as co
@@ -92,11 +93,15 @@ def _oracle_step(n_frames=1):
   opt, model, sd = make_model('coco_tracking')
   orc = co.DLA34Oracle(sd, opt.heads)
   img, pre, hm = wt.synthetic_inputs(1, H, W)
+  done = 0
   t0 = time.perf_counter()
   for _ in range(n_frames):
     out = co.sigmoid_output(orc.forward(img, pre, hm))
     co.generic_decode(out, K)
-  return time.perf_counter() - t0, torch.get_num_threads()
+    done += 1
+    if budget_s is not None and time.perf_counter() - t0 > budget_s:
+      break
+  return time.perf_counter() - t0, torch.get_num_threads(), done
 
 
 def run_reference(args, rank, world):
@@ -110,9 +115,14 @@ def run_reference(args, rank, world):
     _oracle_step(1)
   t, thr = 0.0, 1
   steps = min(args.steps, 6)
+  done = 0
   for _ in range(steps):
-    dt, thr = _oracle_step(frames_per_step)
+    dt, thr, _n = _oracle_step(frames_per_step)
     t += dt
+    done += 1
+    if t > 60.0:                                        # bounded sample on any host
+      break
+  steps = done
   fps = steps * frames_per_step / t
   line = {'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus,
           'steps': steps, 'warmup': min(args.warmup, 1), 'ms_per_step': 1000 * t / steps,
@@ -324,8 +334,7 @@ def main():
   if not args.no_cpu_baseline and world == 1:       # rank 0 at N=1 only
     _use_host_threads()
     _oracle_step(1)                                     # warm-up (oneDNN primitive caches)
-    n = 10                                              # ~10 s of wall clock on the box's 64 host threads
-    dt, thr = _oracle_step(n)
+    dt, thr, n = _oracle_step(10, budget_s=15.0)        # ~10 s of wall clock on the box's 64 host threads
     cpu = {'value': n / dt, 'unit': 'frames/s', 'cores': thr, 'kind': 'port',
            'sample': '%d frames 512x512 (oracle/ct_oracle.py, torch-CPU fp32)' % n}
 
