@@ -79,3 +79,25 @@ def test_host_weight_packing_roundtrip(built_lib):
       assert tiles[s, r, chunk, j % 8] == wk_bf16[r, kk]
   assert lib.ct_pack_weights(L.CT_ENGINE_TCGEN05, w.ctypes.data, O, I, k, k, 20, dst.ctypes.data) != 0
   assert b'n_tile' in lib.ct_last_error()
+
+
+def test_product_path_refuses_to_run_without_a_gpu(built_lib):
+  """No CPU fallback anywhere on the product path: every public entry point raises on host tensors / no device."""
+  import sys
+  import pytest
+  import torch
+  sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+  from helpers import make_model, make_opt
+  from centertrack_b200.dcn import DCN
+  from centertrack_b200.decode import generic_decode
+  from centertrack_b200.detector import Detector
+  opt, model, _ = make_model('coco_tracking')
+  z = torch.zeros(1, 3, 64, 96)
+  with pytest.raises(RuntimeError, match='no CPU fallback'):
+    model(z, z, torch.zeros(1, 1, 64, 96))
+  with pytest.raises(RuntimeError, match='no CPU fallback'):
+    generic_decode({'hm': torch.rand(1, 2, 8, 8), 'reg': torch.rand(1, 2, 8, 8), 'wh': torch.rand(1, 2, 8, 8)}, K=4)
+  with pytest.raises(RuntimeError, match='no CPU fallback'):
+    DCN(64, 64)(torch.zeros(1, 64, 8, 8))
+  with pytest.raises(RuntimeError, match='no CPU fallback'):
+    Detector(make_opt('coco_tracking', ['--gpus', '-1']))
