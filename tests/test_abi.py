@@ -101,3 +101,21 @@ def test_product_path_refuses_to_run_without_a_gpu(built_lib):
     DCN(64, 64)(torch.zeros(1, 64, 8, 8))
   with pytest.raises(RuntimeError, match='no CPU fallback'):
     Detector(make_opt('coco_tracking', ['--gpus', '-1']))
+
+
+def test_argument_validation_returns_status_without_touching_the_gpu(built_lib):
+  """Every entry point validates before it launches: bad descriptors come back as a negative ct_status with a
+  message in ct_last_error(), nothing throws across the ABI (checked here on a machine with no GPU)."""
+  import sys
+  sys.path.insert(0, ROOT)
+  from centertrack_b200 import _lib as L
+  lib = L.lib()
+  assert lib.ct_decode(ctypes.byref(L.DecodeDesc()), None) == -1 and b'null pointer' in lib.ct_last_error()
+  assert lib.ct_conv_forward(ctypes.byref(L.ConvDesc()), None) == -1 and b'ct_conv_forward' in lib.ct_last_error()
+  p = ctypes.c_void_p(16)
+  assert lib.ct_upsample_add(p, None, p, p, L.CT_BF16, 1, 4, 4, 8, 3, 8, 8, 8, None) == -1
+  assert b'upsample factor' in lib.ct_last_error()
+  assert lib.ct_upsample_add(p, None, p, p, L.CT_BF16, 1, 4, 4, 12, 2, 12, 12, 12, None) == -1     # C % 8 != 0
+  assert lib.ct_packed_weight_bytes(L.CT_ENGINE_TCGEN05, 64, 64, 3, 3, 24) == -1                     # n_tile % 16
+  assert lib.ct_packed_weight_bytes(L.CT_ENGINE_TCGEN05, 64, 64, 3, 3, 64) == 64 * (9 * 64) * 2
+  assert lib.ct_decode_workspace_bytes(2, 80, 0, 100) == 256 + 8 * 2 * 80 * 100
