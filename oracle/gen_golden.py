@@ -74,29 +74,64 @@ def gen_net():
     print('net', cfg, {k: v.shape for k, v in data.items() if k != 'keys'})
 
 
+E2E_CASES = [  # (file stem, cfg, (H, W), batch the frame is cut from, frame index, input seed)
+    ('e2e_coco_tracking_512', 'coco_tracking', (512, 512), 1, 0, 317),
+    ('e2e_coco_tracking_512_b32f0', 'coco_tracking', (512, 512), 32, 0, 4242),      # the shape bench.py runs:
+    ('e2e_coco_tracking_512_b32f31', 'coco_tracking', (512, 512), 32, 31, 4242),    # first / last frame of 32
+    ('e2e_mot_544x960', 'mot', (544, 960), 1, 0, 317),
+    ('e2e_coco_pose_512', 'coco_pose', (512, 512), 1, 0, 317)]
+E2E_STAGE_POS = 128
+
+
+def e2e_frame(hw, batch, frame, seed):
+  """The (img, pre, hm) of one frame of a `batch`-frame synthetic step (bench.py builds the same batch)."""
+  img, pre, hm = wt.synthetic_inputs(batch, hw[0], hw[1], seed=seed)
+  return img[frame:frame + 1].clone(), pre[frame:frame + 1].clone(), hm[frame:frame + 1].clone()
+
+
 def gen_e2e():
-  """coco_tracking 512x512 through the reference model + _sigmoid_output + generic_decode."""
+  """Full-size frames through the reference model + _sigmoid_output + generic_decode: head values at random
+  positions, the decoded top-K, and every STAGES tensor at E2E_STAGE_POS random positions (all channels)."""
   from model.decode import generic_decode
-  opt, model = rh.build_reference_model('coco_tracking')
-  sd = wt.make_state_dict(model.state_dict(), 317)
-  model.load_state_dict(sd)
-  img, pre, hm = wt.synthetic_inputs(1, 512, 512)
-  with torch.no_grad():
-    out = model(img, pre, hm)[-1]
-    out['hm'] = out['hm'].sigmoid_()
-    out['pre_inds'] = None
-    dets = generic_decode({k: (v.clone() if v is not None else None) for k, v in out.items()}, K=100, opt=opt)
-  rng = np.random.RandomState(3)
-  pos = rng.randint(0, 128 * 128, size=512)
-  data = {'pos': pos}
-  for k in ('hm', 'reg', 'wh', 'tracking'):
-    v = out[k].numpy().reshape(out[k].shape[1], -1)
-    data['sample.' + k] = v[:, pos]
-  data.update({'det.' + k: v.numpy() for k, v in dets.items()})
-  hmn = out['hm'].numpy()
-  data['hm_max_per_class'] = hmn.reshape(80, -1).max(1)
-  np.savez_compressed(os.path.join(OUT, 'e2e_coco_tracking_512.npz'), **data)
-  print('e2e', {k: v.shape for k, v in data.items()})
+  models = {}
+  for stem, cfg, hw, batch, frame, seed in E2E_CASES:
+    if cfg not in models:
+      opt, model = rh.build_reference_model(cfg, input_hw=hw)
+      sd = wt.make_state_dict(model.state_dict(), 317)
+      model.load_state_dict(sd)
+      models[cfg] = (opt, model)
+    opt, model = models[cfg]
+    img, pre, hm = e2e_frame(hw, batch, frame, seed)
+    acts, hooks = {}, []
+    mods = dict(model.named_modules())
+    for name in STAGES:
+      hooks.append(mods[name].register_forward_hook(
+          lambda m, i, o, name=name: acts.__setitem__(name, o.detach().clone())))
+    with torch.no_grad():
+      out = model(img, pre, hm)[-1]
+      for h in hooks:
+        h.remove()
+      out['hm'] = out['hm'].sigmoid_()
+      if 'hm_hp' in out:
+        out['hm_hp'] = out['hm_hp'].sigmoid_()
+      out['pre_inds'] = None
+      dets = generic_decode({k: (v.clone() if v is not None else None) for k, v in out.items()}, K=100, opt=opt)
+    oh, ow = hw[0] // 4, hw[1] // 4
+    rng = np.random.RandomState(3)
+    pos = rng.randint(0, oh * ow, size=512)
+    data = {'pos': pos}
+    for k, v in out.items():
+      if v is not None:
+        data['sample.' + k] = v.numpy().reshape(v.shape[1], -1)[:, pos]
+    data.update({'det.' + k: v.numpy() for k, v in dets.items()})
+    data['hm_max_per_class'] = out['hm'].numpy().reshape(out['hm'].shape[1], -1).max(1)
+    for name, t in acts.items():
+      n = t.shape[2] * t.shape[3]
+      sp = np.random.RandomState(5).randint(0, n, size=min(E2E_STAGE_POS, n))
+      data['stagepos.' + name] = sp
+      data['stage.' + name] = t.numpy().reshape(t.shape[1], -1)[:, sp]
+    np.savez_compressed(os.path.join(OUT, stem + '.npz'), **data)
+    print('e2e', stem, len(data), 'arrays', 'top score %.4f .. %.4f' % (float(dets['scores'][0, 0]), float(dets['scores'][0, -1])))
 
 
 def gen_decode():
