@@ -50,19 +50,7 @@ def _round_up(v, m):
 class Detector(object):
 
   def __init__(self, opt):
-    if opt.gpus[0] < 0 or not torch.cuda.is_available():
-      raise RuntimeError('centertrack_b200.Detector needs a CUDA device (B200, sm_100a); there is no '
-                         'CPU fallback (got --gpus %s)' % getattr(opt, 'gpus_str', opt.gpus))
-    if opt.flip_test:
-      raise NotImplementedError('--flip_test is scheduled after the main path (SURVEY 8f-3)')
-    opt.device = torch.device('cuda')
-    print('Creating model...')
-    model = create_model(opt.arch, opt.heads, opt.head_conv, opt=opt)
-    if opt.load_model:
-      model = load_model(model, opt.load_model, opt)
-    else:
-      print('Warning: no --load_model given; running with randomly initialised weights')
-    self.model = model.to(opt.device).eval()
+    self.model = self._init_device_model(opt)
     self.opt = opt
     ds = self.trained_dataset = get_dataset(opt.dataset)
     self.mean = np.asarray(ds.mean, dtype=np.float32).reshape(1, 1, 3)
@@ -74,6 +62,21 @@ class Detector(object):
     self.pre_images = None
     self.pre_image_ori = None
     self.tracker = Tracker(opt)
+
+  @staticmethod
+  def _init_device_model(opt):
+    """detector.py:26-36: pick the device, build the network, load the checkpoint.  No CPU fallback."""
+    if opt.gpus[0] < 0 or not torch.cuda.is_available():
+      raise RuntimeError('centertrack_b200.Detector needs a CUDA device (B200, sm_100a); there is no '
+                         'CPU fallback (got --gpus %s)' % getattr(opt, 'gpus_str', opt.gpus))
+    opt.device = torch.device('cuda')
+    print('Creating model...')
+    model = create_model(opt.arch, opt.heads, opt.head_conv, opt=opt)
+    if opt.load_model:
+      model = load_model(model, opt.load_model, opt)
+    else:
+      print('Warning: no --load_model given; running with randomly initialised weights')
+    return model.to(opt.device).eval()
 
   # ------------------------------------------------------------------------------------ run
   def _open_input(self, source):
@@ -135,7 +138,27 @@ class Detector(object):
     clock.lap('track')
     self.cnt += 1
     clock.acc['display'] += time.time() - t_merged        # the reference's display span starts at the merge mark
-    return clock.report(results)
+    ret = clock.report(results)
+    if getattr(self.opt, 'save_video', False):            # detector.py:162-165: the frame demo.py writes to the video
+      ret['generic'] = self._render_generic(image, results)
+    return ret
+
+  def _render_generic(self, image, results):
+    """Stand-in for Debugger's 'generic' canvas (detector.py:379-445, out of the hot-path scope): the input frame with
+    each result's box and `class[:tracking id] score` label.  BGR uint8, same size as the input frame."""
+    import cv2
+    canvas = np.ascontiguousarray(image).copy()
+    for r in results:
+      if r['score'] <= getattr(self.opt, 'vis_thresh', 0.3):
+        continue
+      x0, y0, x1, y1 = [int(round(float(v))) for v in r['bbox'][:4]]
+      tid = int(r.get('tracking_id', 0))
+      colour = ((37 * tid) % 255, (17 * tid + 80) % 255, (29 * tid + 160) % 255)
+      cv2.rectangle(canvas, (x0, y0), (x1, y1), colour, 2)
+      label = '%d:%d %.2f' % (int(r['class']), tid, float(r['score'])) if 'tracking_id' in r else \
+          '%d %.2f' % (int(r['class']), float(r['score']))
+      cv2.putText(canvas, label, (x0, max(0, y0 - 3)), cv2.FONT_HERSHEY_SIMPLEX, 0.5, colour, 1, cv2.LINE_AA)
+    return canvas
 
   # ------------------------------------------------------------------------------------ host pre
   def _input_geometry(self, height, width, scale):

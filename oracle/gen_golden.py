@@ -18,7 +18,7 @@ import ref_harness as rh          # noqa
 sys.path.insert(0, os.path.join(HERE, '..'))
 from centertrack_b200 import synthetic as wt   # noqa
 
-OUT = os.path.join(HERE, '..', 'tests', 'golden')
+OUT = os.environ.get('CT_GOLDEN_OUT') or os.path.join(HERE, '..', 'tests', 'golden')
 SMALL_HW = (64, 96)
 STAGES = ['base.level2', 'base.level3', 'base.level4', 'base.level5', 'dla_up.ida_0.proj_1',
           'dla_up.ida_0.node_1', 'dla_up.ida_1.node_2', 'dla_up.ida_2.node_3', 'ida_up.node_1', 'ida_up.node_2']

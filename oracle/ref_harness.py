@@ -82,15 +82,12 @@ def _stub(name, **attrs):
 _installed = False
 
 
-def install():
-  """Make `import detector`, `import model.model`, ... resolve to the reference."""
-  global _installed
-  if _installed:
-    return
-  if not available():
-    raise RuntimeError('reference checkout not present at %s' % REF_ROOT)
+def install_third_party_stubs():
+  """Stub modules for the packages the reference imports but this image lacks (all off the arithmetic path)."""
 
   class _Bar(object):
+    suffix = ''
+    elapsed_td = eta_td = 0
     def __init__(self, *a, **k): pass
     def next(self): pass
     def finish(self): pass
@@ -125,6 +122,15 @@ def install():
     _stub('torchvision.models.utils',
           load_state_dict_from_url=torch.hub.load_state_dict_from_url)
 
+
+def install():
+  """Make `import detector`, `import model.model`, ... resolve to the reference."""
+  global _installed
+  if _installed:
+    return
+  if not available():
+    raise RuntimeError('reference checkout not present at %s' % REF_ROOT)
+  install_third_party_stubs()
   pkg = _stub('model.networks.DCNv2')
   pkg.__path__ = []
   _stub('model.networks.DCNv2.dcn_v2', DCN=_RefDCN)
