@@ -32,7 +32,7 @@ class ConvDesc(C.Structure):
       ('OH', C.c_int32), ('OW', C.c_int32), ('ld_out', C.c_int32), ('out_mode', C.c_int32),
       ('relu', C.c_int32), ('ld_res', C.c_int32), ('head_act', C.c_int32),
       ('sig_from', C.c_int32), ('depth_scale', C.c_float), ('ld_om', C.c_int32),
-      ('n_tile', C.c_int32), ('epilogue_sum3', C.c_int32),
+      ('n_tile', C.c_int32), ('epilogue_sum3', C.c_int32), ('pad_w1', C.c_int32),
       ('x', C.c_void_p), ('w', C.c_void_p), ('shift', C.c_void_p), ('residual', C.c_void_p),
       ('om', C.c_void_p), ('out', C.c_void_p),
   ]

@@ -105,7 +105,11 @@ extern "C" int ct_conv_forward(const ct_conv_desc* d, void* stream) {
   CT_REQUIRE(d && d->x && d->w && d->out, "null pointer");
   CT_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->C_in > 0 && d->C_out > 0, "bad shape");
   CT_REQUIRE(d->OH == (d->H + 2 * d->pad - d->KH) / d->stride + 1, "OH inconsistent");
-  CT_REQUIRE(d->OW == (d->W + 2 * d->pad - d->KW) / d->stride + 1, "OW inconsistent");
+  {
+    const int pad_w = d->pad_w1 > 0 ? d->pad_w1 - 1 : d->pad;
+    CT_REQUIRE(d->OW == (d->W + 2 * pad_w - d->KW) / d->stride + 1, "OW inconsistent");
+    CT_REQUIRE(d->pad_w1 == 0 || d->engine != CT_ENGINE_TCGEN05_HALO, "halo engine: square 'same' kernels only");
+  }
   CT_REQUIRE(d->ld_in >= d->C_in, "ld_in < C_in");
   CT_REQUIRE(d->out_mode == CT_OUT_NCHW_F32 || d->ld_out >= (d->epilogue_sum3 ? 16 : d->C_out), "ld_out < C_out");
   if (d->a_mode == CT_A_DCN) {

@@ -7,7 +7,7 @@ namespace ctb {
 
 struct ConvGeom {
   int B, H, W, C_in, ld_in;
-  int C_out, KH, KW, stride, pad, OH, OW;
+  int C_out, KH, KW, stride, pad, pad_w, OH, OW;
   int ld_out, out_mode, relu, ld_res, head_act, sig_from;
   float depth_scale;
   int ld_om;
@@ -19,6 +19,7 @@ inline ConvGeom make_geom(const ct_conv_desc* d) {
   ConvGeom g;
   g.B = d->B; g.H = d->H; g.W = d->W; g.C_in = d->C_in; g.ld_in = d->ld_in;
   g.C_out = d->C_out; g.KH = d->KH; g.KW = d->KW; g.stride = d->stride; g.pad = d->pad;
+  g.pad_w = d->pad_w1 > 0 ? d->pad_w1 - 1 : d->pad;
   g.OH = d->OH; g.OW = d->OW; g.ld_out = d->ld_out; g.out_mode = d->out_mode;
   g.relu = d->relu; g.ld_res = d->ld_res; g.head_act = d->head_act; g.sig_from = d->sig_from;
   g.depth_scale = d->depth_scale; g.ld_om = d->ld_om;

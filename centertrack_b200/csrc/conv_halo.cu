@@ -565,11 +565,10 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
   // operand staging mode: whole-pixel swizzled rows when C_in*2 is a swizzle width (one 32/64/128-byte TMA
   // request per halo pixel); C_in == 8 keeps the 16-byte un-swizzled rows but merges (x, c) in the tensor map
   // when the tensor is dense (ld_in == 8) so that one request covers a whole halo row.
-  const char* env = getenv("CTB_HALO_MODE");   // debug: "planes" forces the un-swizzled plane path
-  const bool force_planes = env && strcmp(env, "planes") == 0;
+  static const bool force_planes = [] { const char* e = getenv("CTB_HALO_MODE"); return e && strcmp(e, "planes") == 0; }();   // debug
   a.swz = (g.C_in > 64) ? 128 : ((!force_planes && (g.C_in == 16 || g.C_in == 32 || g.C_in == 64)) ? g.C_in * 2 : 0);
-  const char* envb = getenv("CTB_HALO_BASEOFF");
-  a.use_base_offset = envb ? atoi(envb) : 0;   // measured on B200: the MMA's swizzle is a pure function of the
+  static const int base_off_env = getenv("CTB_HALO_BASEOFF") ? atoi(getenv("CTB_HALO_BASEOFF")) : 0;
+  a.use_base_offset = base_off_env;   // measured on B200: the MMA's swizzle is a pure function of the
                                                 // shared-memory address (same as the TMA's), no base offset needed
   a.merged_xc = (g.C_in == 8 && g.ld_in == 8) ? 1 : 0;
   a.planes = a.swz ? (g.C_in * 2 + a.swz - 1) / a.swz : g.C_in / 8;   // swizzled: 64-channel chunks
@@ -612,8 +611,10 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
   // Two accumulators per MMA warp when TMEM allows (warp w owns accumulators w and w + 2): a warp can start its next
   // item while the epilogue still drains the previous one (~15 % on the 64-channel layers).
   a.nacc = 4 * n_tile <= 512 ? 4 : 2;
-  { const char* e1 = getenv("CTB_HALO_NACC"); if (e1) a.nacc = atoi(e1); }
-  { const char* e2 = getenv("CTB_HALO_MMA_WARPS"); a.mma_warps = e2 ? atoi(e2) : 2; }
+  static const int nacc_env = getenv("CTB_HALO_NACC") ? atoi(getenv("CTB_HALO_NACC")) : 0;
+  static const int mma_warps_env = getenv("CTB_HALO_MMA_WARPS") ? atoi(getenv("CTB_HALO_MMA_WARPS")) : 2;
+  if (nacc_env) a.nacc = nacc_env;
+  a.mma_warps = mma_warps_env;
   while (cols < a.nacc * n_tile) cols <<= 1;
   if (cols > 512) return fail(CT_ERR_INVALID, "conv_halo: n_tile too large for double-buffered TMEM%s", "");
   a.tmem_cols = cols;
@@ -637,7 +638,8 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
     stages = 3;
     while (stages > 2 && smem_for(stages) > 220 * 1024) --stages;
   }
-  { const char* e3 = getenv("CTB_HALO_STAGES"); if (e3) stages = atoi(e3); }
+  static const int stages_env = getenv("CTB_HALO_STAGES") ? atoi(getenv("CTB_HALO_STAGES")) : 0;
+  if (stages_env) stages = stages_env;
   if (a.mma_warps == 2 && (stages & 1))
     return fail(CT_ERR_INVALID, "conv_halo: two MMA warps need an even number of halo stages%s", "");
   if (smem_for(stages) > 227 * 1024)
@@ -671,15 +673,21 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
   }
   if (cr != CUDA_SUCCESS) return fail(CT_ERR_CUDA, "conv_halo: cuTensorMapEncodeTiled failed%s (%ld)", "", (long)cr);
 
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    CT_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  // persistent grid: a multiple of n_tiles_n, at most (SMs x CTAs that fit) and no more than the work
+  // the attribute is per device (a process may drive several GPUs from one thread)
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static thread_local unsigned long long attr_set_mask = 0;
+  if (dev >= 64 || !((attr_set_mask >> dev) & 1ull)) {
+    CT_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (dev < 64) attr_set_mask |= 1ull << dev;
+  }
+  // persistent grid: a multiple of n_tiles_n, at most (SMs x CTAs that fit) and no more than the work
+  static thread_local int sms_of[64] = {0};
+  if (dev < 64 && sms_of[dev]) sms = sms_of[dev];
+  else {
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (dev < 64) sms_of[dev] = sms;
+  }
   int per_sm = (int)((227 * 1024) / smem);
   const int by_tmem = 512 / cols;
   if (per_sm > by_tmem) per_sm = by_tmem;

@@ -68,7 +68,7 @@ conv_simt_kernel(ConvGeom g, const T* __restrict__ x, const float* __restrict__ 
       const int c = k0 - tap * g.C_in + aq * 4;
       if (AMODE == CT_A_CONV) {
         const int ky = tap / g.KW, kx = tap - ky * g.KW;
-        const int iy = aoy * g.stride - g.pad + ky, ix = aox * g.stride - g.pad + kx;
+        const int iy = aoy * g.stride - g.pad + ky, ix = aox * g.stride - g.pad_w + kx;
         if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
           av = Vec4<T>::ld(xb + ((size_t)iy * g.W + ix) * g.ld_in + c);
       } else {

@@ -245,7 +245,7 @@ conv_tc_kernel(const TcArgs a) {
           const int b = p / HWo, r = p - b * HWo;
           const int oy = r / g.OW, ox = r - oy * g.OW;
           row_iy[i] = oy * g.stride - g.pad;
-          row_ix[i] = ox * g.stride - g.pad;
+          row_ix[i] = ox * g.stride - g.pad_w;
           row_off[i] = (b * g.H * g.W + row_iy[i] * g.W + row_ix[i]) * g.ld_in;
         } else {
           row_off[i] = 0; row_iy[i] = -100000; row_ix[i] = -100000;
@@ -260,7 +260,7 @@ conv_tc_kernel(const TcArgs a) {
       for (int i = 0; i < TC_NROW; ++i) {
         if (p < g.P_out) {
           row_iy[i] = oy * g.stride - g.pad;
-          row_ix[i] = ox * g.stride - g.pad;
+          row_ix[i] = ox * g.stride - g.pad_w;
           row_off[i] = (b * g.H * g.W + row_iy[i] * g.W + row_ix[i]) * g.ld_in;
         } else {
           row_off[i] = 0; row_iy[i] = -100000; row_ix[i] = -100000;
@@ -598,10 +598,14 @@ int conv_forward_tc(const ct_conv_desc* d, cudaStream_t st) {
   if (stages > a.k_slices) stages = a.k_slices;
   a.stages = stages;
   const size_t smem = smem_for(stages);
-  static thread_local size_t smem_set = 0;
-  if (smem > smem_set) {
-    CT_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-    smem_set = 200 * 1024;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static thread_local unsigned long long attr_set_mask = 0;      // the attribute is per device
+    if (dev >= 64 || !((attr_set_mask >> dev) & 1ull)) {
+      CT_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+      if (dev < 64) attr_set_mask |= 1ull << dev;
+    }
   }
   const int n_tiles = (g.C_out + n_tile - 1) / n_tile;
   // Optional 2-D pixel patches (CTB_TC_TILE2D=1) when they tile the map exactly.  Measured on B200: no gain -- the

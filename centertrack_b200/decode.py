@@ -33,7 +33,10 @@ _ws_cache = {}
 
 
 def _workspace(device, B, C_, J, K):
-  key = (str(device), B, C_, J, K)
+  """Scratch of one ct_decode launch (per-batch arrival counters + candidate lists).  Keyed by the CUDA stream as
+  well: two runners / Detectors driving different streams must not share the counters."""
+  import torch as _t
+  key = (str(device), B, C_, J, K, int(_t.cuda.current_stream(device).cuda_stream))
   ws = _ws_cache.get(key)
   if ws is None:
     n = L.lib().ct_decode_workspace_bytes(B, C_, J, K)
@@ -49,7 +52,9 @@ def _f32c(t, name):
   return t if t.is_contiguous() else t.contiguous()
 
 
-def generic_decode(output, K=100, opt=None, records_out=None):
+def generic_decode(output, K=100, opt=None, records_out=None, workspace=None):
+  """`workspace`: optional caller-owned scratch tensor (ct_decode_workspace_bytes, zero-initialised once); a
+  CUDA-graph capture must pass its own so that the captured pointer stays alive and private."""
   if 'hm' not in output:
     return {}
   if opt is not None and getattr(opt, 'zero_tracking', False) and 'tracking' in output:
@@ -105,7 +110,8 @@ def generic_decode(output, K=100, opt=None, records_out=None):
   else:
     assert records_out.shape == (B, K, off) and records_out.is_contiguous()
   d.records = records_out.data_ptr()
-  ws = _workspace(heat.device, B, cat, J, K)
+  ws = workspace if workspace is not None else _workspace(heat.device, B, cat, J, K)
+  assert ws.numel() * ws.element_size() >= L.lib().ct_decode_workspace_bytes(B, cat, J, K)
   d.workspace = ws.data_ptr()
   L.check(L.lib().ct_decode(C.byref(d), L.stream_ptr()), 'ct_decode')
   return views_from_records(records_out, layout, output, W)

@@ -53,8 +53,10 @@ def _pow2_at_least(n):
 class DLA34Engine(object):
 
   def __init__(self, state_dict, heads, B, H, W, precision='bf16', device='cuda',
-               depth_scale=1.0, has_pre_img=True, has_pre_hm=True, use_halo=True):
+               depth_scale=1.0, has_pre_img=True, has_pre_hm=True, use_halo=True, dla_node='dcn'):
     assert precision in ('bf16', 'fp32')
+    assert dla_node in ('dcn', 'conv', 'gcn')
+    self.dla_node = dla_node
     assert H % 32 == 0 and W % 32 == 0, 'DLA-34 needs input sizes divisible by 32'
     self.lib = L.lib()
     self.sd = {k: v.detach().to('cpu', torch.float64) for k, v in state_dict.items()
@@ -132,14 +134,16 @@ class DLA34Engine(object):
     if w.shape[1] != C_in:      # input channels padded (never happens for DLA-34 tensors)
       raise ValueError('%s: C_in mismatch %d vs %d' % (name, w.shape[1], C_in))
     C_out = w.shape[0] if c_out is None else c_out
-    pad = k // 2
-    OH = (x.H + 2 * pad - k) // stride + 1
-    OW = (x.W + 2 * pad - k) // stride + 1
+    kh, kw = (k, k) if isinstance(k, int) else k
+    pad, pad_w = kh // 2, kw // 2
+    OH = (x.H + 2 * pad - kh) // stride + 1
+    OW = (x.W + 2 * pad_w - kw) // stride + 1
     P = self.B * OH * OW
     engine = self.engine
     n_tile = self._pick_n_tile(P, C_out) if engine == L.CT_ENGINE_TCGEN05 else 0
-    if engine == L.CT_ENGINE_TCGEN05 and self.use_halo and a_mode == L.CT_A_CONV and stride == 1 and \
+    if engine == L.CT_ENGINE_TCGEN05 and self.use_halo and a_mode == L.CT_A_CONV and stride == 1 and kh == kw and \
         (C_in in (16, 32, 48, 64, 128, 192, 256) or (C_in == 8 and sum3)):
+      k = kh
       # stride-1 layer whose weights fit in smem: TMA halo tile + descriptor-shifted taps (csrc/conv_halo.cu)
       nblk = k * ((k + 1) // 2) if C_in == 8 else k * k * (C_in // 16)
       halo = C_in * 2 * (8 + k - 1 + (1 if C_in == 8 else 0)) * (16 + k - 1) + 1024 * max(1, C_in // 64)
@@ -152,8 +156,9 @@ class DLA34Engine(object):
     d.engine, d.dtype, d.a_mode = engine, self.ct_dtype, a_mode
     d.epilogue_sum3 = sum3
     d.B, d.H, d.W, d.C_in, d.ld_in, d.C_out = self.B, x.H, x.W, C_in, x.ld, C_out
-    d.KH = d.KW = k
+    d.KH, d.KW = kh, kw
     d.stride, d.pad, d.OH, d.OW = stride, pad, OH, OW
+    d.pad_w1 = 0 if pad_w == pad else pad_w + 1
     d.out_mode, d.relu, d.head_act, d.sig_from = out_mode, int(relu), head_act, sig_from
     d.depth_scale = self.depth_scale
     d.n_tile = n_tile
@@ -202,6 +207,27 @@ class DLA34Engine(object):
     w, shift = self._fold(p + '.conv', p + '.actf.0')
     self._conv(p, x, w, shift, out, 3, 1, relu=True, a_mode=L.CT_A_DCN, om=om)
 
+  def _node(self, p, x, out, which):
+    """IDAUp's proj (which=0) / node (which=1) module by --dla_node (dla.py:588-592): DeformConv | Conv | GlobalConv."""
+    if self.dla_node == 'dcn':
+      return self._deform(p, x, out)
+    if self.dla_node == 'conv' or which == 0:             # Conv (dla.py:466-475): 1x1 conv + BN + ReLU
+      return self._conv_bn(p, x, p + '.conv.0', p + '.conv.1', out, 1)
+    # GlobalConv (dla.py:477-503): relu(bn((1xk o kx1)(x) + (kx1 o 1xk)(x))).  BN is affine, so its scale folds into
+    # the second conv of each branch, its shift into the left branch, and the right branch adds the left as residual.
+    sd = self.sd
+    kk = sd[p + '.gcl.0.weight'].shape[2]
+    s = sd[p + '.act.0.weight'] / torch.sqrt(sd[p + '.act.0.running_var'] + BN_EPS)
+    t = sd[p + '.act.0.bias'] - sd[p + '.act.0.running_mean'] * s
+    zero = torch.zeros(out.C, dtype=torch.float64)
+    t1 = TV(self._buf(x.H, x.W, out.C), 0, out.C)
+    left = TV(self._buf(x.H, x.W, out.C), 0, out.C)
+    t2 = TV(self._buf(x.H, x.W, out.C), 0, out.C)
+    self._conv(p + '.gcl.0', x, sd[p + '.gcl.0.weight'], zero, t1, (kk, 1), 1, relu=False)
+    self._conv(p + '.gcl.1', t1, sd[p + '.gcl.1.weight'] * s.view(-1, 1, 1, 1), t, left, (1, kk), 1, relu=False)
+    self._conv(p + '.gcr.0', x, sd[p + '.gcr.0.weight'], zero, t2, (1, kk), 1, relu=False)
+    return self._conv(p, t2, sd[p + '.gcr.1.weight'] * s.view(-1, 1, 1, 1), zero, out, (kk, 1), 1, relu=True, residual=left)
+
   def _up_add(self, p, x, skip, out, f):
     w = self._dev(self.sd[p + '.weight'].to(torch.float32).reshape(x.C, 2 * f, 2 * f).permute(1, 2, 0).contiguous())
     self.ops.append(('up', (x, skip, w, out, f), p))
@@ -213,13 +239,13 @@ class DLA34Engine(object):
       j = i - startp
       src = layers[i]
       proj = TV(self._buf(src.H, src.W, o), 0, o)
-      self._deform('%s.proj_%d' % (p, j), src, proj)
+      self._node('%s.proj_%d' % (p, j), src, proj, 0)
       upw = self.sd['%s.up_%d.weight' % (p, j)]
       f = upw.shape[2] // 2
       summed = TV(self._buf(src.H * f, src.W * f, o), 0, o)
       self._up_add('%s.up_%d' % (p, j), proj, layers[i - 1], summed, f)
       node = TV(self._buf(src.H * f, src.W * f, o), 0, o)
-      self._deform('%s.node_%d' % (p, j), summed, node)
+      self._node('%s.node_%d' % (p, j), summed, node, 1)
       layers[i] = node
 
   # ------------------------------------------------------------------ plan

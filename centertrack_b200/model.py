@@ -6,7 +6,8 @@
 (dla.py:594-617 + base_model.py:14-65), so reference checkpoints load key-for-key (including the two
 dead `base.level{3,4}.project.*` tensors and BatchNorm's `num_batches_tracked`), but holds no PyTorch
 compute: `forward` hands the state_dict to a `DLA34Engine` plan of libctb200 launches.
-Only `dla_34` (the default --arch, opts.py:82) with `--dla_node dcn` is built; other archs raise.
+Only `dla_34` (the default --arch, opts.py:82) is built -- with any `--dla_node` (dcn | conv | gcn, dla.py:588-592);
+other archs raise.
 """
 import torch
 import torch.nn as nn
@@ -78,6 +79,25 @@ def _deform(cin, cout):                        # DeformConv keys: actf.0, conv (
   return m
 
 
+def _conv_node(cin, cout):                     # Conv keys (dla.py:466-475): conv.0 (1x1), conv.1 (BN)
+  m = _Holder()
+  m.conv = nn.Sequential(nn.Conv2d(cin, cout, 1, bias=False), _bn(cout), nn.ReLU(inplace=True))
+  return m
+
+
+def _global_conv_node(cin, cout, k=7):         # GlobalConv keys (dla.py:477-503): gcl.{0,1}, gcr.{0,1}, act.0
+  m = _Holder()
+  m.gcl = nn.Sequential(nn.Conv2d(cin, cout, (k, 1), bias=False, padding=(k // 2, 0)),
+                        nn.Conv2d(cout, cout, (1, k), bias=False, padding=(0, k // 2)))
+  m.gcr = nn.Sequential(nn.Conv2d(cin, cout, (1, k), bias=False, padding=(0, k // 2)),
+                        nn.Conv2d(cout, cout, (k, 1), bias=False, padding=(k // 2, 0)))
+  m.act = nn.Sequential(_bn(cout), nn.ReLU(inplace=True))
+  return m
+
+
+DLA_NODE = {'dcn': (_deform, _deform), 'gcn': (_conv_node, _global_conv_node), 'conv': (_conv_node, _conv_node)}
+
+
 def _fill_up_weights(up):
   """Bilinear initialisation of the (learnable) depthwise upsampling kernel (dla.py:454-463)."""
   w = up.weight.data
@@ -89,15 +109,15 @@ def _fill_up_weights(up):
   w[:] = (g[:, None] * g[None, :]).to(w.dtype)
 
 
-def _ida(o, channels, up_f):                   # IDAUp keys: proj_i, up_i, node_i
+def _ida(o, channels, up_f, node_type=(_deform, _deform)):    # IDAUp keys: proj_i, up_i, node_i
   m = _Holder()
   for i in range(1, len(channels)):
     f = int(up_f[i])
-    setattr(m, 'proj_%d' % i, _deform(channels[i], o))
+    setattr(m, 'proj_%d' % i, node_type[0](channels[i], o))
     up = nn.ConvTranspose2d(o, o, f * 2, stride=f, padding=f // 2, output_padding=0, groups=o, bias=False)
     _fill_up_weights(up)
     setattr(m, 'up_%d' % i, up)
-    setattr(m, 'node_%d' % i, _deform(o, o))
+    setattr(m, 'node_%d' % i, node_type[1](o, o))
   return m
 
 
@@ -108,8 +128,7 @@ class DLASegB200(nn.Module):
     super(DLASegB200, self).__init__()
     if num_layers != 34:
       raise NotImplementedError('only DLA-34 (arch dla_34) is on the B200 hot path')
-    if opt is not None and getattr(opt, 'dla_node', 'dcn') != 'dcn':
-      raise NotImplementedError('--dla_node %s is out of scope (dcn only)' % opt.dla_node)
+    node_type = DLA_NODE[getattr(opt, 'dla_node', 'dcn') if opt is not None else 'dcn']      # dla.py:588-592
     self.opt = opt
     self.heads = heads
     self.num_stacks = 1
@@ -135,11 +154,11 @@ class DLASegB200(nn.Module):
     scales = [1, 2, 4, 8]
     for i in range(3):
       j = -i - 2
-      setattr(dla_up, 'ida_%d' % i, _ida(channels[j], in_ch[j:], [s // scales[j] for s in scales[j:]]))
+      setattr(dla_up, 'ida_%d' % i, _ida(channels[j], in_ch[j:], [s // scales[j] for s in scales[j:]], node_type))
       scales[j + 1:] = [scales[j]] * len(scales[j + 1:])
       in_ch[j + 1:] = [channels[j]] * len(in_ch[j + 1:])
     self.dla_up = dla_up
-    self.ida_up = _ida(64, ch[2:5], [1, 2, 4])
+    self.ida_up = _ida(64, ch[2:5], [1, 2, 4], node_type)
     # heads (base_model.py:23-65)
     for head in heads:
       classes, hc = heads[head], head_convs[head]
@@ -174,15 +193,27 @@ class DLASegB200(nn.Module):
   def invalidate(self):
     self._engines = {}
 
+  MAX_ENGINES = 4       # resolutions kept alive (each holds a full activation plan on the GPU); LRU beyond that
+
+  def _weights_version(self):
+    """Changes whenever a parameter/buffer is written in place (tensor._version) or replaced (.half(), .to())."""
+    return tuple((id(t), t._version, t.dtype) for t in list(self.parameters()) + list(self.buffers()))
+
   def engine_for(self, B, H, W, device, precision=None):
     precision = precision or self.precision
+    ver = self._weights_version()
+    if getattr(self, '_engines_version', None) != ver:        # in-place weight edits / dtype moves: repack
+      self._engines = {}
+      self._engines_version = ver
     key = (B, H, W, str(device), precision)
-    eng = self._engines.get(key)
+    eng = self._engines.pop(key, None)
     if eng is None:
       depth_scale = getattr(self.opt, 'depth_scale', 1.0) if self.opt is not None else 1.0
       eng = DLA34Engine(self.state_dict(), self.heads, B, H, W, precision=precision, device=device,
-                        depth_scale=depth_scale)
-      self._engines[key] = eng
+                        depth_scale=depth_scale, dla_node=getattr(self.opt, 'dla_node', 'dcn') if self.opt is not None else 'dcn')
+      while len(self._engines) >= self.MAX_ENGINES:           # --keep_res / --fix_short on variable-size inputs
+        self._engines.pop(next(iter(self._engines)))
+    self._engines[key] = eng                                  # most recently used last
     return eng
 
   def forward(self, x, pre_img=None, pre_hm=None):

@@ -66,11 +66,20 @@ class opts(object):
     a('--resume', action='store_true')
     a('--lr', type=float, default=1.25e-4)
     a('--lr_step', type=str, default='60')
-    a('--b200_precision', default='bf16', choices=['bf16', 'fp32'])
+    # loss weights: a head whose weight is 0 is not built (opts.py:366-369), so they shape the network
+    for flag, default in (('hm_weight', 1), ('off_weight', 1), ('wh_weight', 0.1), ('hp_weight', 1),
+                          ('hm_hp_weight', 1), ('amodel_offset_weight', 1), ('dep_weight', 1), ('dim_weight', 1),
+                          ('rot_weight', 1), ('tracking_weight', 1), ('nuscenes_att_weight', 1),
+                          ('velocity_weight', 1)):
+      a('--' + flag, type=float, default=default)
+    a('--b200_precision', default='bf16', choices=['bf16', 'fp32', 'bf16x3'])
     self.parser = p
 
   def parse(self, args=''):
-    opt, _ignored = self.parser.parse_known_args() if args == '' else self.parser.parse_known_args(args)
+    opt, ignored = self.parser.parse_known_args() if args == '' else self.parser.parse_known_args(args)
+    if ignored:     # training / logging / visualisation flags of the reference are accepted; say so, a typo must be visible
+      print('centertrack_b200.opts: ignoring arguments outside the inference path: %s' % ' '.join(ignored))
+    opt.ignored_args = ignored
     if opt.test_dataset == '':
       opt.test_dataset = opt.dataset
     opt.gpus_str = opt.gpus
@@ -112,6 +121,13 @@ class opts(object):
                   (opt.ltrb, (('ltrb', 4),)), (opt.ltrb_amodal, (('ltrb_amodal', 4),)),
                   (opt.nuscenes_att, (('nuscenes_att', 8),)), (opt.velocity, (('velocity', 3),))]
     opt.heads = {name: ch for enabled, group in head_table if enabled for name, ch in group}
+    weight_of = {'hm': opt.hm_weight, 'wh': opt.wh_weight, 'reg': opt.off_weight, 'hps': opt.hp_weight,
+                 'hm_hp': opt.hm_hp_weight, 'hp_offset': opt.off_weight, 'dep': opt.dep_weight, 'rot': opt.rot_weight,
+                 'dim': opt.dim_weight, 'amodel_offset': opt.amodel_offset_weight, 'ltrb': opt.ltrb_weight,
+                 'tracking': opt.tracking_weight, 'ltrb_amodal': opt.ltrb_amodal_weight,
+                 'nuscenes_att': opt.nuscenes_att_weight, 'velocity': opt.velocity_weight}
+    opt.weights = {name: weight_of[name] for name in opt.heads}
+    opt.heads = {name: ch for name, ch in opt.heads.items() if opt.weights[name] != 0}   # opts.py:366-369
     width = opt.head_conv
     opt.head_conv = {name: [width] * (1 if name == 'reg' else opt.num_head_conv) for name in opt.heads}
     return opt

@@ -121,10 +121,13 @@ class StreamRunner(object):
     self.t += 1
     return prev
 
-  def fetch(self):
-    """Blocks until the last submitted step finished; returns its records as numpy [B,K,F]."""
+  def fetch(self, copy=True):
+    """Blocks until the last submitted step finished; returns its records as numpy [B,K,F].  A copy by default: the
+    two pinned buffers are reused by the asynchronous D2H of later steps (copy=False hands out the pinned view, valid
+    until the step after next is submitted)."""
     self.compute.synchronize()
-    return self.h_rec[(self.t - 1) & 1].numpy()
+    rec = self.h_rec[(self.t - 1) & 1].numpy()
+    return rec.copy() if copy else rec
 
   @property
   def h2d_bytes_per_step(self):

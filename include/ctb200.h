@@ -88,6 +88,8 @@ typedef struct {
   int32_t n_tile;        /* tcgen05: output-channel tile (multiple of 16, <= 256); 0 = auto */
   int32_t epilogue_sum3; /* HALO engine, C_out == 48: out16 = sum over present groups g (bit g set) of
                             relu(acc[16g..16g+15] + shift) -- the three DLA stems (dla.py:307-311) */
+  int32_t pad_w1;        /* 0: horizontal padding = pad; else horizontal padding + 1 (the (k,1) / (1,k) convs of
+                            GlobalConv, dla.py:477-503; SIMT and gather engines) */
   const void* x;         /* input activations */
   const void* w;         /* packed weights: see ct_pack_weights */
   const float* shift;    /* [C_out] folded BN shift / conv bias (may be NULL) */

@@ -21,14 +21,18 @@ from centertrack_b200.opts import opts                 # noqa: E402
 
 
 def main(seed=317):
-  opt = opts().init(['tracking', '--pre_hm'])
-  template = create_model(opt.arch, opt.heads, opt.head_conv, opt=opt).state_dict()
-  sd = syn.make_state_dict(template, seed, calibrated=False)
-  orc = co.DLA34Oracle(sd, opt.heads)
-  orc.calibrate = True
-  img, pre, hm = syn.synthetic_inputs(1, 128, 160, seed=seed + 1)
-  orc.feats(img, pre, hm)
-  stats = {k: orc.sd[k].numpy() for k in sd if k.endswith('running_mean') or k.endswith('running_var')}
+  stats = {}
+  for node in ('dcn', 'conv', 'gcn'):                   # the trunk statistics are shared; every node kind adds its own BNs
+    opt = opts().init(['tracking', '--pre_hm', '--dla_node', node])
+    template = create_model(opt.arch, opt.heads, opt.head_conv, opt=opt).state_dict()
+    sd = syn.make_state_dict(template, seed, calibrated=False)
+    orc = co.DLA34Oracle(sd, opt.heads, dla_node=node)
+    orc.calibrate = True
+    img, pre, hm = syn.synthetic_inputs(1, 128, 160, seed=seed + 1)
+    orc.feats(img, pre, hm)
+    for k in sd:
+      if (k.endswith('running_mean') or k.endswith('running_var')) and k not in stats:
+        stats[k] = orc.sd[k].numpy()
   os.makedirs(os.path.dirname(syn.calib_path(seed)), exist_ok=True)
   np.savez_compressed(syn.calib_path(seed), **stats)
   print('wrote', syn.calib_path(seed), len(stats), 'arrays')

@@ -51,8 +51,9 @@ DECODE_CASES = [('coco', 1, 80, 128, 128, 100, 11), ('mot', 1, 1, 136, 240, 100,
 
 
 def gen_net():
-  for cfg in ['coco_tracking', 'mot', 'nuscenes_ddd', 'coco_pose']:
-    opt, model = rh.build_reference_model(cfg, input_hw=SMALL_HW)
+  for cfg, node in [('coco_tracking', 'dcn'), ('mot', 'dcn'), ('nuscenes_ddd', 'dcn'), ('coco_pose', 'dcn'),
+                    ('coco_tracking', 'conv'), ('coco_tracking', 'gcn')]:          # --dla_node (dla.py:588-592)
+    opt, model = rh.build_reference_model(cfg, input_hw=SMALL_HW, extra=['--dla_node', node])
     sd = wt.make_state_dict(model.state_dict(), 317)
     model.load_state_dict(sd)
     img, pre, hm = wt.synthetic_inputs(1, *SMALL_HW)
@@ -70,8 +71,9 @@ def gen_net():
     data = {'head.' + k: v.numpy() for k, v in out.items()}
     data.update({'stage.' + k: v.numpy() for k, v in acts.items()})
     data['keys'] = np.array(sorted(sd.keys()))
-    np.savez_compressed(os.path.join(OUT, 'net_%s_64x96.npz' % cfg), **data)
-    print('net', cfg, {k: v.shape for k, v in data.items() if k != 'keys'})
+    stem = 'net_%s_64x96.npz' % cfg if node == 'dcn' else 'net_%s_%s_64x96.npz' % (cfg, node)
+    np.savez_compressed(os.path.join(OUT, stem), **data)
+    print('net', cfg, node, {k: v.shape for k, v in data.items() if k != 'keys'})
 
 
 E2E_CASES = [  # (file stem, cfg, (H, W), batch the frame is cut from, frame index, input seed)
@@ -218,12 +220,15 @@ OPT_CASES = [['tracking'], ['tracking', '--pre_hm', '--track_thresh', '0.4', '--
              ['tracking,ddd', '--pre_hm', '--nuscenes_att', '--velocity', '--input_res', '640'],
              ['tracking,multi_pose', '--keep_res', '--K', '50', '--num_head_conv', '2'],
              ['ctdet', '--head_conv', '128', '--test_scales', '1', '--fix_short', '512', '--out_thresh', '0.2'],
-             ['tracking', '--no_pre_img', '--zero_pre_hm', '--zero_tracking', '--max_age', '3', '--new_thresh', '0.6']]
+             ['tracking', '--no_pre_img', '--zero_pre_hm', '--zero_tracking', '--max_age', '3', '--new_thresh', '0.6'],
+             ['tracking,multi_pose', '--hm_hp_weight', '0', '--hp_weight', '0', '--pre_hm'],      # zero-weight heads are not built
+             ['tracking,ddd', '--dep_weight', '0', '--flip_test', '--dla_node', 'conv']]
 OPT_FIELDS = ['task', 'dataset', 'test_dataset', 'arch', 'heads', 'head_conv', 'num_classes', 'input_h', 'input_w',
               'output_h', 'output_w', 'input_res', 'output_res', 'down_ratio', 'pad', 'num_stacks', 'fix_res', 'fix_short',
               'tracking', 'pre_img', 'pre_hm', 'zero_pre_hm', 'zero_tracking', 'out_thresh', 'pre_thresh', 'new_thresh',
               'track_thresh', 'max_age', 'K', 'test_scales', 'head_kernel', 'prior_bias', 'ltrb', 'ltrb_amodal',
-              'nuscenes_att', 'velocity', 'depth_scale', 'flip_test', 'public_det', 'hungarian', 'model_output_list']
+              'nuscenes_att', 'velocity', 'depth_scale', 'flip_test', 'public_det', 'hungarian', 'model_output_list', 'weights',
+              'dla_node']
 
 
 def gen_opts():

@@ -212,12 +212,12 @@ def he_init_(model, seed=317, hm_scale=0.25):
   return model
 
 
-def build_reference_model(cfg='coco_tracking', seed=317, ckpt_path=None, input_hw=None):
+def build_reference_model(cfg='coco_tracking', seed=317, ckpt_path=None, input_hw=None, extra=()):
   """create_model (model.py:24-29) + He init + save_model (model.py:92-101)."""
   install()
   import io, contextlib
   from model.model import create_model, save_model
-  opt = make_opt(cfg, load_model='dummy.pth', input_hw=input_hw)
+  opt = make_opt(cfg, load_model='dummy.pth', input_hw=input_hw, extra=extra)
   with contextlib.redirect_stdout(io.StringIO()):
     model = create_model(opt.arch, opt.heads, opt.head_conv, opt=opt)
   he_init_(model, seed)

@@ -15,14 +15,16 @@ from centertrack_b200 import synthetic as wt
 from helpers import DECODE_CASES, HOST_CASES, decode_inputs, host_case_inputs, make_opt, make_model
 
 
-@pytest.mark.parametrize('cfg', ['coco_tracking', 'mot', 'nuscenes_ddd', 'coco_pose'])
+@pytest.mark.parametrize('cfg', ['coco_tracking', 'mot', 'nuscenes_ddd', 'coco_pose', 'coco_tracking_conv',
+                                 'coco_tracking_gcn'])
 def test_oracle_network_matches_reference_golden(cfg, golden_dir):
   g = np.load(os.path.join(golden_dir, 'net_%s_64x96.npz' % cfg))
-  opt, model, sd = make_model(cfg)
+  node = cfg.rsplit('_', 1)[1] if cfg.endswith(('_conv', '_gcn')) else 'dcn'       # --dla_node (dla.py:588-592)
+  opt, model, sd = make_model(cfg[:-len(node) - 1] if node != 'dcn' else cfg, extra=['--dla_node', node])
   assert sorted(sd.keys()) == list(g['keys'])          # state-dict key compatibility
   img, pre, hm = wt.synthetic_inputs(1, 64, 96)
   trace = {}
-  out = co.DLA34Oracle(sd, opt.heads).forward(img, pre, hm, trace=trace)
+  out = co.DLA34Oracle(sd, opt.heads, dla_node=node).forward(img, pre, hm, trace=trace)
   for k in out:
     ref = g['head.' + k]
     assert out[k].shape == ref.shape
