@@ -1,12 +1,15 @@
 #!/usr/bin/env python
 """bench.py -- CenterTrack per-frame inference hot path on B200 (contract: see DESIGN.md section 6).
 
-  python bench.py --gpus N --steps K --warmup W [--batch B] [--impl reference]
+  python bench.py --gpus N --steps K --warmup W [--batch B] [--config CFG] [--precision P] [--impl reference]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1]): DLA-34 coco_tracking, 512x512, bf16, synthetic frame pairs +
-pre_hm, K=100.  One step = the hot path (network + fused sigmoid + fused decode) over one batch of B
-frames per GPU.  metric = frames/sec, whole job.  Prints ONE JSON line on rank 0.
+Workload (default = BASELINE.json configs[1]): DLA-34 coco_tracking, 512x512, bf16, synthetic frame pairs, K=100.
+--config mot | nuscenes_ddd | coco_pose selects BASELINE configs 3-5 (960x544 / 800x448 / 512x512 pose heads).
+One step = the hot path over one batch of B frames (B independent streams) per GPU:
+    prior heat-map splat from the streams' tracks -> DLA-34 + DCNv2 neck + heads (+ fused sigmoid) -> fused decode
+    (NMS + top-K + gathers) -> greedy displacement association,   all on the device, one CUDA graph.
+metric = frames/sec, whole job.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -22,10 +25,21 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 
-METRIC = 'frames/sec (device-timed) DLA-34 512x512'
-GFLOP_PER_FRAME = 72.56          # algorithmic, BASELINE.md section 2 (coco_tracking 512x512)
-H = W = 512
 K = 100
+# name -> (H, W, algorithmic GFLOP per frame (SURVEY 8d / BASELINE.md section 2), BASELINE.json config index)
+CONFIGS = {'coco_tracking': (512, 512, 72.56, 1), 'mot': (544, 960, 143.23, 2),
+           'nuscenes_ddd': (448, 800, 124.98, 3), 'coco_pose': (512, 512, 86.84, 4)}
+
+
+def metric_name(cfg):
+  H, W = CONFIGS[cfg][:2]
+  return 'frames/sec (device-timed) DLA-34 %dx%d' % (W, H) if cfg != 'coco_tracking' else \
+      'frames/sec (device-timed) DLA-34 512x512'
+
+
+def workload_name(cfg):
+  H, W, _, idx = CONFIGS[cfg]
+  return 'DLA-34 %s %dx%d frame pairs + pre_hm, K=%d (BASELINE configs[%d])' % (cfg, W, H, K, idx)
 
 
 def _peaks():
@@ -81,23 +95,30 @@ def _use_host_threads():
     torch.set_num_threads(n)
 
 
-def _oracle_step(n_frames=1, budget_s=None):
-  """The CPU restatement of the reference path (oracle/), timed on this host: network + sigmoid +
-  decode for up to n_frames 512x512 frame pairs (stops early once budget_s seconds have elapsed, so a slow or
-  oversubscribed host cannot stall the bench).  Returns (seconds, threads, frames done)."""
+def _oracle_step(cfg, n_frames=1, budget_s=None):
+  """The CPU restatement of the reference path (oracle/), timed on this host: network + sigmoid + decode +
+  post-process + greedy association for up to n_frames frame pairs of the config's size (stops early once budget_s
+  seconds have elapsed).  Returns (seconds, threads, frames done)."""
   sys.path.insert(0, os.path.join(ROOT, 'oracle'))
   sys.path.insert(0, os.path.join(ROOT, 'tests'))
   import ct_oracle as co
   from centertrack_b200 import synthetic as wt
   from helpers import make_model
-  opt, model, sd = make_model('coco_tracking')
+  H, W = CONFIGS[cfg][:2]
+  opt, model, sd = make_model(cfg)
   orc = co.DLA34Oracle(sd, opt.heads)
+  trk = co.TrackerOracle(opt.new_thresh)
+  trk.init_track([])
   img, pre, hm = wt.synthetic_inputs(1, H, W)
+  c = np.array([W / 2., H / 2.], np.float32)
   done = 0
   t0 = time.perf_counter()
   for _ in range(n_frames):
     out = co.sigmoid_output(orc.forward(img, pre, hm))
-    co.generic_decode(out, K)
+    dets = {k: v for k, v in co.generic_decode(out, K).items() if not k.startswith('_')}
+    if 'dep' not in dets:                                   # ddd post-process needs calibration: association only for 2-D
+      res = co.generic_post_process(dets, [c], [max(H, W) * 1.0], H // 4, W // 4, opt.out_thresh)[0]
+      trk.step([r for r in res if r['score'] > opt.out_thresh])
     done += 1
     if budget_s is not None and time.perf_counter() - t0 > budget_s:
       break
@@ -112,27 +133,26 @@ def run_reference(args, rank, world):
   _use_host_threads()
   frames_per_step = 1
   for _ in range(min(args.warmup, 1)):
-    _oracle_step(1)
+    _oracle_step(args.config, 1)
   t, thr = 0.0, 1
   steps = min(args.steps, 6)
   done = 0
   for _ in range(steps):
-    dt, thr, _n = _oracle_step(frames_per_step)
+    dt, thr, _n = _oracle_step(args.config, frames_per_step)
     t += dt
     done += 1
     if t > 60.0:                                        # bounded sample on any host
       break
   steps = done
   fps = steps * frames_per_step / t
-  line = {'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus,
+  line = {'impl': 'reference', 'metric': metric_name(args.config), 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus,
           'steps': steps, 'warmup': min(args.warmup, 1), 'ms_per_step': 1000 * t / steps,
           'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
           'data': 'synthetic',
-          'config': {'workload': 'DLA-34 coco_tracking 512x512 frame pairs + pre_hm, K=100 (BASELINE configs[1])',
-                     'frames_per_step': frames_per_step},
+          'config': {'workload': workload_name(args.config), 'frames_per_step': frames_per_step},
           'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': thr, 'kind': 'port',
                            'sample': '%d steps x %d frame (oracle/ct_oracle.py: torch-CPU fp32 convs + '
-                                     'restated DCNv2/decode)' % (steps, frames_per_step)},
+                                     'restated DCNv2/decode/association)' % (steps, frames_per_step)},
           'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
   _emit(line)
 
@@ -150,15 +170,142 @@ def _emit(line):
     os.write(_REAL_STDOUT, data)
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# per-kernel time inside the step (roofline shares)
+# ------------------------------------------------------------------------------------------------------------------
+def _op_flops(kind, pl, L):
+  if kind != 'conv':
+    return 0.0
+  if pl.epilogue_sum3:
+    return 2.0 * pl.B * pl.OH * pl.OW * 16 * 49 * 7            # the three stems: 16 x (3+3+1) x 7x7 MACs/pixel
+  return 2.0 * pl.B * pl.OH * pl.OW * pl.C_out * pl.KH * pl.KW * pl.C_in
+
+
+def _op_group(kind, pl, L):
+  if kind != 'conv':
+    return kind
+  if pl.a_mode == L.CT_A_DCN:
+    return 'dcn_main'
+  return {L.CT_ENGINE_TCGEN05: 'conv_tc', L.CT_ENGINE_TCGEN05_HALO: 'conv_halo', L.CT_ENGINE_SIMT: 'conv_simt'}[pl.engine]
+
+
+def per_op_times(runner, L, reps=5):
+  """Per-launch device time of one step IN ITS REAL ORDER AND CACHE STATE: the step is captured once more into a CUDA
+  graph with an (external, timing) event-record node after every launch; consecutive differences over `reps` replays.
+  Falls back to the CUPTI kernel records of torch.profiler, then to one event pair per eager launch.
+  -> (method, [ms per op of eng.ops], decode_ms, tracker_ms or None)"""
+  eng = runner.eng
+  n = len(eng.ops)
+  slot = 1
+  img, pre, hm = runner.img[slot], runner.img[(slot - 1) % 3], runner.hm[slot]
+  img_p, pre_p, hm_p = L.ptr(img), L.ptr(pre if eng.has_pre_img else None), L.ptr(hm if eng.has_pre_hm else None)
+  from centertrack_b200.decode import generic_decode
+
+  def run_marked(marks):
+    k = 0
+    marks[k].record(); k += 1
+    if runner.tracker is not None:
+      runner.tracker.render(hm)
+    marks[k].record(); k += 1
+    st = L.stream_ptr()
+    for kind, pl, name in eng.ops:
+      eng._run_one(kind, pl, name, img_p, pre_p, hm_p, st)
+      marks[k].record(); k += 1
+    generic_decode(dict(eng.outputs), K=runner.K, records_out=runner.rec, workspace=runner.ws)
+    marks[k].record(); k += 1
+    if runner.tracker is not None:
+      runner.tracker.step(runner.rec)
+    marks[k].record(); k += 1
+
+  def collect(marks):
+    d = [marks[i].elapsed_time(marks[i + 1]) for i in range(len(marks) - 1)]
+    return d[1:1 + n], d[1 + n], (d[0] + d[2 + n]) if runner.tracker is not None else None
+
+  n_marks = n + 4
+  try:
+    marks = [torch.cuda.Event(enable_timing=True, external=True) for _ in range(n_marks)]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+      run_marked([torch.cuda.Event(enable_timing=True) for _ in range(n_marks)])
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+      run_marked(marks)
+    acc, dec, trk = np.zeros(n), 0.0, 0.0
+    for _ in range(reps):
+      g.replay()
+      torch.cuda.synchronize()
+      a, b, c = collect(marks)
+      acc += np.array(a); dec += b; trk += (c or 0.0)
+    return 'graph-event-nodes', list(acc / reps), dec / reps, (trk / reps if runner.tracker is not None else None)
+  except Exception as e:                                      # noqa: BLE001
+    sys.stderr.write('per_op_times: graph event nodes unavailable (%s); eager event pairs\n' % (e,))
+  acc, dec, trk = np.zeros(n), 0.0, 0.0
+  for _ in range(reps):
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(n_marks)]
+    run_marked(marks)
+    torch.cuda.synchronize()
+    a, b, c = collect(marks)
+    acc += np.array(a); dec += b; trk += (c or 0.0)
+  return 'eager-event-pairs', list(acc / reps), dec / reps, (trk / reps if runner.tracker is not None else None)
+
+
+def parity_at_bench_shape(runner, cfg, B, H, W, precision, wt):
+  """The engine that was just timed, at the shape it was timed at, against the reference's fp32 outputs
+  (tests/golden/e2e_*.npz): errors of frames 0 and B-1 of a seeded batch (tests/parity.py metrics)."""
+  sys.path.insert(0, os.path.join(ROOT, 'tests'))
+  import parity as P
+  gold = os.path.join(ROOT, 'tests', 'golden')
+  if cfg == 'coco_tracking' and B == 32:
+    cases = [('e2e_coco_tracking_512_b32f0', 0), ('e2e_coco_tracking_512_b32f31', 31)]
+    seed, batch = 4242, 32
+  else:
+    stem = {'coco_tracking': 'e2e_coco_tracking_512', 'mot': 'e2e_mot_544x960', 'coco_pose': 'e2e_coco_pose_512'}.get(cfg)
+    if stem is None:
+      return None
+    cases, seed, batch = [(stem, 0)], 317, 1
+  img, pre, hm = wt.synthetic_inputs(batch, H, W, seed=seed)
+  if batch < B:                                              # frame 0 is the golden's frame; the rest of the batch is filler
+    rep = lambda t: t.expand(B, *t.shape[1:]).contiguous()
+    img, pre, hm = rep(img), rep(pre), rep(hm)
+  eng = runner.eng
+  dev = runner.device
+  from centertrack_b200.decode import generic_decode
+  out = dict(eng.forward(img.to(dev), pre.to(dev), hm.to(dev)))
+  dets = generic_decode(out, K=K, workspace=runner.ws)
+  torch.cuda.synchronize(dev)
+  d = {k: dets[k].cpu().numpy() for k in ('clses', 'xs', 'ys')}
+  res = {'engine': precision, 'against': 'reference fp32 outputs, tests/golden (oracle/gen_golden.py)', 'frames': {}}
+  worst = {}
+  for stem, frame in cases:
+    g = np.load(os.path.join(gold, stem + '.npz'))
+    m = P.summarize(P.head_metrics(out, g, frame), P.peak_metrics(out, d, g, frame), P.stage_metrics(eng.stage, g, frame))
+    res['frames'][stem] = m
+    for k in ('score_max', 'bbox_max', 'tracking_max'):
+      if k in m:
+        worst[k] = max(worst.get(k, 0.0), m[k])
+    worst['head_max'] = max(worst.get('head_max', 0.0), max(m['head_max'].values()))
+    worst['stage_max'] = max(worst.get('stage_max', 0.0), max(m['stage_max'].values()))
+    worst['topk_overlap'] = min(worst.get('topk_overlap', 1.0), m['topk_overlap'])
+  res['worst'] = worst
+  return res
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
   ap.add_argument('--steps', type=int, default=30)
   ap.add_argument('--warmup', type=int, default=5)
   ap.add_argument('--batch', type=int, default=32, help='frames (independent streams) per GPU per step')
+  ap.add_argument('--config', default='coco_tracking', choices=sorted(CONFIGS))
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-  ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+  ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32', 'bf16x3'])
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-parity', action='store_true')
+  ap.add_argument('--no-latency', action='store_true')
+  ap.add_argument('--host-tracking', action='store_true',
+                  help='round-1 mode: pre_hm supplied by the host, no association on the device')
   args = ap.parse_args()
   # stdout carries exactly ONE JSON line: everything any library writes to fd 1 during the run (NCCL prints a version
   # banner there) is sent to stderr, and the result line goes to the saved descriptor (see _emit)
@@ -186,19 +333,21 @@ def main():
   from centertrack_b200 import synthetic as wt
   from helpers import make_model
   from centertrack_b200 import _lib as L
-  from centertrack_b200.runner import StreamRunner
+  from centertrack_b200.runner import NS, StreamRunner
 
+  cfg = args.config
+  H, W, gflop_per_frame, _ = CONFIGS[cfg]
   B = args.batch
-  opt, model, sd = make_model('coco_tracking')
+  opt, model, sd = make_model(cfg)
   model = model.to(dev)
-  runner = StreamRunner(model, B, H, W, K=K, precision=args.precision, device=dev)
-  # synthetic inputs: 2 slots x B distinct frames (+ pre_hm); inputs alone are 2 x B x 4.2 MB and one step
-  # streams ~0.3 GB of activations per frame, so nothing but the 40 MB of weights can live in the 126 MB L2
+  tracking = not args.host_tracking
+  runner = StreamRunner(model, B, H, W, K=K, precision=args.precision, device=dev, opt=opt, device_tracking=tracking)
+  # synthetic inputs: 2 distinct frames per stream (+ pre_hm in host-tracking mode); inputs alone are 2 x B x 3-4 MB
+  # and one step streams ~0.3 GB of activations per frame, so nothing but the 40 MB of weights can live in the 126 MB L2
   img, pre, hm = wt.synthetic_inputs(2, H, W, seed=317 + rank)
   g = torch.Generator().manual_seed(rank)
   host_img = [(img[s:s + 1] + 0.05 * torch.randn(B, 3, H, W, generator=g)).pin_memory() for s in range(2)]
   host_hm = [hm[s:s + 1].expand(B, 1, H, W).contiguous().pin_memory() for s in range(2)]
-  from centertrack_b200.runner import NS
   for s in range(NS):
     runner.load_device_inputs(host_img[s & 1].to(dev), host_hm[s & 1].to(dev), s)
   runner.warm()
@@ -208,13 +357,14 @@ def main():
       dist.barrier()
     torch.cuda.synchronize(dev)
 
-  gathered = torch.empty((world * B,) + tuple(runner.rec.shape[1:]), device=dev) if world > 1 else None
+  gather_src = runner.tracker.tracks if tracking else runner.rec
+  gathered = torch.empty((world * B,) + tuple(gather_src.shape[1:]), device=dev) if world > 1 else None
 
   # ---------------- device-resident timing (value) ----------------
   def dev_step():
     runner.step_device()
     if gathered is not None:               # the one collective of the path: fixed-size result gather
-      dist.all_gather_into_tensor(gathered, runner.rec)
+      dist.all_gather_into_tensor(gathered, gather_src)
 
   for _ in range(args.warmup):
     dev_step()
@@ -237,15 +387,22 @@ def main():
   ms_per_step = ms / args.steps
   value = world * B * args.steps / (ms / 1000.0)
 
-  # ---------------- end-to-end timing (host buffers in, host records out) ----------------
+  # ---------------- end-to-end timing (host frames in, host records + tracks out) ----------------
+  def host_step(i):
+    if tracking:
+      runner.step_host(host_img[i & 1])
+    else:
+      runner.step_host(host_img[i & 1], host_hm[i & 1])
+
   for i in range(args.warmup):
-    runner.step_host(host_img[i & 1], host_hm[i & 1])
+    host_step(i)
   runner.fetch()
   barrier()
   t0 = time.perf_counter()
   for i in range(args.steps):
-    runner.step_host(host_img[i & 1], host_hm[i & 1])
+    host_step(i)
   rec_last = runner.fetch()
+  n_tracks_last = int(runner.fetch_tracks()[1][:, 0].sum()) if tracking else None
   barrier()
   e2e_s = time.perf_counter() - t0
   if dist is not None:
@@ -259,99 +416,132 @@ def main():
       dist.destroy_process_group()
     return
 
-  # ---------------- roofline of the dominant kernel (conv_tc_kernel), measured live ----------------
-  # `traffic`: dram__bytes_read.sum + dram__bytes_write.sum of these launches from the committed ncu --set full capture
-  # of one step at 32 frames/step (profiles/r01f_ncu_tc_raw.csv: 2157.5 + 381.1 MB over the 40 launches;
-  # profiles/r01f_ncu_halo_raw.csv: 3058.0 + 1848.4 MB over the 34 launches), scaled by frames per step.
-  NCU_DRAM_BYTES_PER_FRAME = {'conv_tc': 2538.59e6 / 32, 'conv_halo': 4906.37e6 / 32}
+  # ---------------- roofline: per-kernel time inside the step, measured live ----------------
+  # `traffic`: dram__bytes_read.sum + dram__bytes_write.sum from the committed ncu --set full capture of one step at
+  # 32 frames/step (profiles/), scaled by frames per step; null for configs without a capture.
   eng = runner.eng
-  stream = torch.cuda.current_stream()
-  conv_ms, conv_flop, all_ms, halo_ms, halo_flop = 0.0, 0.0, 0.0, 0.0, 0.0
-  reps = 3
-  per_kind = {}
-  for rep in range(reps):
-    marks = [torch.cuda.Event(enable_timing=True) for _ in range(len(eng.ops) + 1)]
-    marks[0].record()
-    st = L.stream_ptr()
-    for i, (kind, pl, name) in enumerate(eng.ops):
-      eng._run_one(kind, pl, name, L.ptr(runner.img[0]), L.ptr(runner.img[1]), L.ptr(runner.hm[0]), st)
-      marks[i + 1].record()
-    torch.cuda.synchronize(dev)
-    for i, (kind, pl, name) in enumerate(eng.ops):
-      dt = marks[i].elapsed_time(marks[i + 1])
-      all_ms += dt
-      key = 'dcn' if (kind == 'conv' and pl.a_mode == L.CT_A_DCN) else kind
-      per_kind[key] = per_kind.get(key, 0.0) + dt / reps
-      fl = 2.0 * pl.B * pl.OH * pl.OW * pl.C_out * pl.KH * pl.KW * pl.C_in if kind == 'conv' else 0.0
-      if kind == 'conv' and pl.epilogue_sum3:
-        fl = 2.0 * pl.B * pl.OH * pl.OW * 16 * 49 * 7            # the three stems: 16 x (3+3+1) x 7x7 MACs/pixel
-      if kind == 'conv' and pl.engine == L.CT_ENGINE_TCGEN05:
-        conv_ms += dt
-        conv_flop += fl
-      if kind == 'conv' and pl.engine == L.CT_ENGINE_TCGEN05_HALO:
-        halo_ms += dt
-        halo_flop += fl
-  conv_ms /= reps
-  conv_flop /= reps
-  halo_ms /= reps
-  halo_flop /= reps
-  all_ms /= reps
-  # decode-only latency: the fused NMS + top-K + gather launch on the maps the last step left in HBM
-  from centertrack_b200.decode import generic_decode
-  dec_out = dict(eng.forward(runner.img[0], runner.img[1], runner.hm[0]))
-  for _ in range(3):
-    generic_decode(dec_out, K=K, records_out=runner.rec)
-  d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  d0.record()
-  for _ in range(10):
-    generic_decode(dec_out, K=K, records_out=runner.rec)
-  d1.record()
-  torch.cuda.synchronize(dev)
-  decode_us = d0.elapsed_time(d1) * 1000.0 / 10
-  hm_bytes = float(dec_out['hm'].numel() * 4)
+  method, op_ms, decode_ms, tracker_ms = per_op_times(runner, L)
+  raw_sum = sum(op_ms) + decode_ms + (tracker_ms or 0.0)
+  rescaled = False
+  if raw_sum > 1.05 * ms_per_step:          # the marked replay ran slower than the plain one (event nodes, eager launch
+    f = ms_per_step / raw_sum               # gaps): attribute the excess proportionally so that the shares add up
+    op_ms, decode_ms = [x * f for x in op_ms], decode_ms * f
+    tracker_ms = tracker_ms * f if tracker_ms is not None else None
+    rescaled = True
+  groups = {}
+  for (kind, pl, name), dt in zip(eng.ops, op_ms):
+    gname = _op_group(kind, pl, L)
+    gr = groups.setdefault(gname, {'ms': 0.0, 'flop': 0.0, 'launches': 0})
+    gr['ms'] += dt
+    gr['flop'] += _op_flops(kind, pl, L)
+    gr['launches'] += 1
+  sum_ms = sum(op_ms) + decode_ms + (tracker_ms or 0.0)
   peak_tf, peak_hbm, peak_src = _peaks()
-  achieved = conv_flop / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
-  halo_tf = halo_flop / (halo_ms / 1000.0) / 1e12 if halo_ms > 0 else 0.0
-  roofline = {'kernel': 'conv_tc_kernel (all %d gather-engine tcgen05 conv/DCN launches of one step)' %
-              sum(1 for k, p, n in eng.ops if k == 'conv' and p.engine == L.CT_ENGINE_TCGEN05),
-              'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
-              'frac': achieved / peak_tf if peak_tf else None,
-              'traffic': NCU_DRAM_BYTES_PER_FRAME['conv_tc'] * B if args.precision == 'bf16' else None,
-              'traffic_unit': 'bytes per step (all launches of the kernel), ncu capture at 32 frames/step scaled',
-              'peak_source': peak_src,
-              'share_of_step': conv_ms / all_ms if all_ms else None,
-              'second_kernel': {'kernel': 'conv_halo_kernel (%d launches)' % sum(1 for k, p, n in eng.ops if k == 'conv' and p.engine == L.CT_ENGINE_TCGEN05_HALO),
-                                'achieved': halo_tf, 'frac': halo_tf / peak_tf if peak_tf else None,
-                                'traffic': NCU_DRAM_BYTES_PER_FRAME['conv_halo'] * B if args.precision == 'bf16' else None,
-                                'share_of_step': halo_ms / all_ms if all_ms else None},
-              'eager_ms_by_kind': {k: round(v, 3) for k, v in per_kind.items()},
-              'decode': {'us_per_launch': round(decode_us, 1), 'frames': B, 'bound': 'hbm',
-                         'achieved': hm_bytes / (decode_us * 1e-6) / 1e9, 'peak': peak_hbm, 'unit': 'GB/s',
-                         'frac': (hm_bytes / (decode_us * 1e-6) / 1e9) / peak_hbm if peak_hbm else None},
-              'whole_step_tflops': GFLOP_PER_FRAME * B / ms_per_step}
+  traffic_per_frame = {}
+  tp = os.path.join(ROOT, 'profiles', 'traffic.json')
+  if os.path.exists(tp):
+    traffic_per_frame = json.load(open(tp)).get(cfg if args.precision == 'bf16' else '', {})
+
+  def tensor_roof(gname, label):
+    gr = groups.get(gname)
+    if not gr or gr['ms'] <= 0:
+      return None
+    ach = gr['flop'] / (gr['ms'] / 1000.0) / 1e12
+    tr = traffic_per_frame.get(gname)
+    return {'kernel': label % gr['launches'], 'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s',
+            'frac': ach / peak_tf if peak_tf else None, 'traffic': tr * B if tr is not None else None,
+            'ms_per_step': round(gr['ms'], 4), 'share_of_step': gr['ms'] / sum_ms, 'gflop_per_step': gr['flop'] / 1e9}
+
+  dcn = tensor_roof('dcn_main', 'conv_tc_kernel, CT_A_DCN (%d DCNv2 launches of one step)')
+  tc = tensor_roof('conv_tc', 'conv_tc_kernel, plain gather (%d stride-2 / deep-layer launches)')
+  halo = tensor_roof('conv_halo', 'conv_halo_kernel (%d launches)')
+  simt = tensor_roof('conv_simt', 'conv_simt_kernel (%d launches)')
+  # dominant kernel = conv_tc_kernel (plain + DCN launches), as in round 1, with its two populations split out below
+  both_ms = sum(groups.get(k, {'ms': 0})['ms'] for k in ('dcn_main', 'conv_tc'))
+  both_fl = sum(groups.get(k, {'flop': 0})['flop'] for k in ('dcn_main', 'conv_tc'))
+  hm_bytes = float(eng.outputs['hm'].numel() * 4 + (eng.outputs['hm_hp'].numel() * 4 if 'hm_hp' in eng.outputs else 0))
+  dec_gbs = hm_bytes / (decode_ms * 1e-3) / 1e9 if decode_ms > 0 else 0.0
+  if both_ms > 0:
+    ach = both_fl / (both_ms / 1000.0) / 1e12
+    t_all = [traffic_per_frame.get(k) for k in ('dcn_main', 'conv_tc')]
+    roofline = {'kernel': 'conv_tc_kernel (all %d gather-engine tcgen05 conv/DCN launches of one step)' %
+                sum(groups.get(k, {'launches': 0})['launches'] for k in ('dcn_main', 'conv_tc')),
+                'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                'frac': ach / peak_tf if peak_tf else None,
+                'traffic': (sum(t_all) * B) if all(t is not None for t in t_all) else None,
+                'share_of_step': both_ms / sum_ms}
+  else:                                                       # fp32 SIMT engine
+    roofline = dict(simt or {})
+  roofline.update({
+      'traffic_unit': 'bytes per step (all launches of the kernel), ncu capture at 32 frames/step scaled',
+      'peak_source': peak_src, 'method': method,
+      'kernels': {'dcn_main': dcn, 'conv_tc_plain': tc, 'conv_halo': halo, 'conv_simt': simt},
+      'ms_by_group': {k: round(v['ms'], 4) for k, v in groups.items()},
+      'sum_kernel_ms': round(raw_sum, 4), 'ms_per_step': round(ms_per_step, 4),
+      'sum_over_step': raw_sum / ms_per_step, 'rescaled_to_step': rescaled,
+      'decode': {'us_per_launch': round(decode_ms * 1000, 1), 'frames': B, 'bound': 'hbm', 'achieved': dec_gbs,
+                 'peak': peak_hbm, 'unit': 'GB/s', 'frac': dec_gbs / peak_hbm if peak_hbm else None},
+      'whole_step_tflops': gflop_per_frame * B / ms_per_step,
+      'whole_step_frac': gflop_per_frame * B / ms_per_step / peak_tf if peak_tf else None})
+  assert sum_ms <= 1.05 * ms_per_step, 'per-kernel times (%.3f ms) do not add up to the step (%.3f ms)' % (sum_ms, ms_per_step)
+
+  # ---------------- parity of the engine that was timed, at the timed shape ----------------
+  parity = None
+  if not args.no_parity:
+    try:
+      parity = parity_at_bench_shape(runner, cfg, B, H, W, args.precision, wt)
+    except Exception as e:                                    # noqa: BLE001
+      parity = {'error': repr(e)}
+
+  # ---------------- per-image latency: Detector.process at B=1 (the reference's only published figure) ----------------
+  latency = None
+  if not args.no_latency:
+    from centertrack_b200.detector import Detector
+    det = Detector.__new__(Detector)
+    opt1 = make_model(cfg, extra=['--b200_precision', args.precision])[0]
+    det.opt, det.model = opt1, model
+    model.precision = args.precision
+    i1, p1, h1 = wt.synthetic_inputs(1, H, W, seed=5)
+    i1, p1, h1 = i1.to(dev), p1.to(dev), h1.to(dev)
+    for _ in range(5):
+      det.process(i1, p1, h1, None)
+    t0 = time.perf_counter()
+    n_lat = 30
+    for _ in range(n_lat):
+      det.process(i1, p1, h1, None)
+    lat_ms = (time.perf_counter() - t0) / n_lat * 1000.0
+    latency = {'ms_per_image': round(lat_ms, 3), 'what': 'Detector.process, 1 frame pair + pre_hm, inputs on device, '
+               'graph replay + fused decode + one D2H of the records; wall clock incl. both synchronisations',
+               'reference_published_ms': 30.0, 'reference_published_on': 'Titan Xp (BASELINE.md)'}
 
   cpu = None
   if not args.no_cpu_baseline and world == 1:       # rank 0 at N=1 only
     _use_host_threads()
-    _oracle_step(1)                                     # warm-up (oneDNN primitive caches)
-    dt, thr, n = _oracle_step(10, budget_s=15.0)        # ~10 s of wall clock on the box's 64 host threads
+    _oracle_step(cfg, 1)                                # warm-up (oneDNN primitive caches)
+    dt, thr, n = _oracle_step(cfg, 10, budget_s=15.0)   # ~10-15 s of wall clock on the box's host threads
     cpu = {'value': n / dt, 'unit': 'frames/s', 'cores': thr, 'kind': 'port',
-           'sample': '%d frames 512x512 (oracle/ct_oracle.py, torch-CPU fp32)' % n}
+           'sample': '%d frames %dx%d (oracle/ct_oracle.py, torch-CPU fp32 + restated decode/association)' % (n, W, H)}
 
-  line = {'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+  line = {'metric': metric_name(cfg), 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
           'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
           'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic',
-          'config': {'workload': 'DLA-34 coco_tracking 512x512 frame pairs + pre_hm, K=100 (BASELINE configs[1])',
+          'config': {'workload': workload_name(cfg),
                      'frames_per_step_per_gpu': B, 'global_batch': B * world,
-                     'parallelism': 'stream-sharded replicas x%d, NCCL all_gather of records' % world,
+                     'parallelism': 'stream-sharded replicas x%d, NCCL all_gather of the result tables' % world,
+                     'step': ('prior heat-map splat from device-resident tracks + network + decode + greedy association '
+                              '(one CUDA graph)') if tracking else 'network + decode, pre_hm given (one CUDA graph)',
                      'l2': 'no flush: per-step inputs %.0f MB in 3 rotating slots + ~%.1f GB of activations per '
-                           'step exceed the 126 MB L2' % (2 * B * 4 * H * W * 4 / 1e6, 0.29 * B),
+                           'step exceed the 126 MB L2' % (2 * B * 3 * H * W * 4 / 1e6, 0.29 * B * H * W / 262144.),
                      'cuda_graph': True},
           'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': runner.h2d_bytes_per_step,
-                  'd2h_bytes_per_step': runner.d2h_bytes_per_step},
+                  'd2h_bytes_per_step': runner.d2h_bytes_per_step,
+                  'what': 'pinned host frames -> H2D -> step -> D2H of records + track tables, every step, '
+                          'reference dependency chain (pre_hm(t) from tracks(t-1)) kept on the device'},
           'gpu_launches': int(runner.launches_per_step * args.steps),
-          'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
-          'check': {'top_score_frame0': float(rec_last[0, 0, 0])}}
+          'decode_us': round(decode_ms * 1000, 1),
+          'tracker_us': round(tracker_ms * 1000, 1) if tracker_ms is not None else None,
+          'clocks': clocks, 'roofline': roofline, 'parity': parity, 'latency': latency, 'cpu_baseline': cpu,
+          'check': {'top_score_frame0': float(rec_last[0, 0, 0]), 'tracks_last_step': n_tracks_last}}
   _emit(line)
   if dist is not None:
     dist.destroy_process_group()

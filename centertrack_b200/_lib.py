@@ -10,7 +10,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libctb200.so')
 CSRC = os.path.join(_HERE, 'csrc')
-SOURCES = ['api.cu', 'conv_simt.cu', 'conv_tc.cu', 'conv_halo.cu', 'elementwise.cu', 'decode.cu']
+SOURCES = ['api.cu', 'conv_simt.cu', 'conv_tc.cu', 'conv_halo.cu', 'elementwise.cu', 'decode.cu', 'stream.cu']
 
 # ---- enums (mirror include/ctb200.h) ----
 CT_F32, CT_BF16 = 0, 1
@@ -54,9 +54,25 @@ class DecodeDesc(C.Structure):
   ]
 
 
+CT_TRK_SCORE, CT_TRK_CLASS, CT_TRK_CT, CT_TRK_TRACKING, CT_TRK_BBOX, CT_TRK_ID, CT_TRK_AGE, CT_TRK_ACTIVE = \
+    0, 1, 2, 4, 6, 10, 11, 12
+CT_TRK_FLOATS = 13
+
+
+class TrackDesc(C.Structure):
+  _fields_ = [
+      ('B', C.c_int32), ('K', C.c_int32), ('F', C.c_int32), ('rec_tracking', C.c_int32),
+      ('max_tracks', C.c_int32), ('out_thresh', C.c_float), ('new_thresh', C.c_float), ('pre_thresh', C.c_float),
+      ('max_age', C.c_int32), ('inp_h', C.c_int32), ('inp_w', C.c_int32),
+      ('records', C.c_void_p), ('trans_out_inv', C.c_void_p), ('trans_input', C.c_void_p),
+      ('tracks', C.c_void_p), ('counts', C.c_void_p), ('boxes', C.c_void_p),
+  ]
+
+
 EXPORTS = ['ct_packed_weight_bytes', 'ct_pack_weights', 'ct_conv_forward', 'ct_stem_forward',
            'ct_pack_stem_input', 'ct_maxpool2', 'ct_upsample_add', 'ct_decode_workspace_bytes', 'ct_decode',
-           'ct_render_pre_hm', 'ct_last_error', 'ct_abi_version', 'ct_launch_count',
+           'ct_render_pre_hm', 'ct_track_smem_bytes', 'ct_track_step', 'ct_render_tracks', 'ct_flip_merge',
+           'ct_warp_affine_normalize', 'ct_last_error', 'ct_abi_version', 'ct_launch_count',
            'ct_reset_launch_count', 'ct_debug_trace', 'ct_debug_watch']
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
@@ -106,6 +122,12 @@ def lib():
   L.ct_decode_workspace_bytes.argtypes = [C.c_int32] * 4
   L.ct_decode.argtypes = [C.POINTER(DecodeDesc), C.c_void_p]
   L.ct_render_pre_hm.argtypes = [C.c_void_p, C.c_int32, C.c_void_p] + [C.c_int32] * 3 + [C.c_void_p]
+  L.ct_track_smem_bytes.restype = C.c_int64
+  L.ct_track_smem_bytes.argtypes = [C.c_int32] * 2
+  L.ct_track_step.argtypes = [C.POINTER(TrackDesc), C.c_void_p]
+  L.ct_render_tracks.argtypes = [C.c_void_p, C.c_int32, C.c_void_p] + [C.c_int32] * 3 + [C.c_void_p]
+  L.ct_flip_merge.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int32] * 3 + [C.c_void_p, C.c_void_p, C.c_void_p]
+  L.ct_warp_affine_normalize.argtypes = [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 4 + [C.c_int32] * 2 + [C.c_void_p]
   L.ct_launch_count.restype = C.c_int64
   L.ct_reset_launch_count.restype = None
   L.ct_debug_trace.argtypes = [C.c_void_p]

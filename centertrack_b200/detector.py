@@ -8,11 +8,15 @@ What differs underneath (`process`, detector.py:335-354): the network is a plan 
 launch, and the 7-13 per-key blocking D2H copies become one copy of the packed record buffer.
 Visualisation (`Debugger`, opt.debug >= 1) is outside the hot-path scope and is ignored.
 """
+import ctypes as C
 import math
+import os
 import time
 
 import numpy as np
 import torch
+
+from . import _lib as L
 
 from .dataset_info import get_dataset
 from .decode import generic_decode
@@ -62,6 +66,7 @@ class Detector(object):
     self.pre_images = None
     self.pre_image_ori = None
     self.tracker = Tracker(opt)
+    self._graphs = {}
 
   @staticmethod
   def _init_device_model(opt):
@@ -118,7 +123,8 @@ class Detector(object):
     per_scale = []
     for scale in self.opt.test_scales:
       if packed is None:
-        images, meta = self.pre_process(image, scale, meta)
+        pre = self.pre_process_device if getattr(self.opt, 'b200_device_pre', False) else self.pre_process
+        images, meta = pre(image, scale, meta)
       else:
         images, meta = self._scale_entry(packed, scale)
       images = images.to(self.opt.device, non_blocking=self.opt.non_block_test)
@@ -200,7 +206,47 @@ class Detector(object):
     to_output = get_affine_transform(c, s, 0, [out_w, out_h])
     warped = cv2.warpAffine(resized, to_input, (inp_w, inp_h), flags=cv2.INTER_LINEAR)
     chw = ((warped / 255. - self.mean) / self.std).astype(np.float32).transpose(2, 0, 1)
-    images = torch.from_numpy(chw.reshape(1, 3, inp_h, inp_w))
+    images = chw.reshape(1, 3, inp_h, inp_w)
+    if self.opt.flip_test:                                  # detector.py:225-226
+      images = np.concatenate((images, images[:, :, :, ::-1]), axis=0)
+    images = torch.from_numpy(np.ascontiguousarray(images))
+    calib = np.array(input_meta['calib'], dtype=np.float32) if 'calib' in input_meta \
+        else self._get_default_calib(width, height)
+    meta = dict(calib=calib, c=c, s=s, height=height, width=width, out_height=out_h, out_width=out_w,
+                inp_height=inp_h, inp_width=inp_w, trans_input=to_input, trans_output=to_output)
+    meta.update({k: input_meta[k] for k in ('pre_dets', 'cur_dets') if k in input_meta})
+    return images, meta
+
+  def pre_process_device(self, image, scale, input_meta={}):
+    """the same contract as `pre_process`, with the per-pixel work -- cv2.warpAffine(INTER_LINEAR),
+    (x/255 - mean)/std, HWC -> CHW -- done by ct_warp_affine_normalize on the GPU from the raw uint8 frame (the
+    geometry stays on the host; `pre_process` itself must remain CPU-only and fork-safe for test.py's DataLoader).
+    Returns CUDA `images`."""
+    height, width = image.shape[:2]
+    (sh, sw), c, s, inp_w, inp_h = self._input_geometry(height, width, 1)     # hazard H5: scale is not forwarded
+    if (sh, sw) != (height, width):
+      import cv2
+      image = cv2.resize(image, (sw, sh))
+    out_w, out_h = inp_w // self.opt.down_ratio, inp_h // self.opt.down_ratio
+    to_input = get_affine_transform(c, s, 0, [inp_w, inp_h])
+    to_output = get_affine_transform(c, s, 0, [out_w, out_h])
+    M = np.asarray(to_input, np.float64).reshape(6).copy()                   # cv::warpAffine inverts the map like this
+    D = M[0] * M[4] - M[1] * M[3]
+    D = 1. / D if D != 0 else 0.
+    A11, A22 = M[4] * D, M[0] * D
+    M[0] = A11; M[1] *= -D; M[3] *= -D; M[4] = A22
+    b1, b2 = -M[0] * M[2] - M[1] * M[5], -M[3] * M[2] - M[4] * M[5]
+    M[2], M[5] = b1, b2
+    dev = self.opt.device
+    src = torch.from_numpy(np.ascontiguousarray(image)).to(dev, non_blocking=True)
+    minv = torch.from_numpy(M.reshape(1, 6)).to(dev)
+    out = torch.empty((1, 3, inp_h, inp_w), dtype=torch.float32, device=dev)
+    mean = np.ascontiguousarray(self.mean.reshape(3), dtype=np.float32)
+    std = np.ascontiguousarray(self.std.reshape(3), dtype=np.float32)
+    L.check(L.lib().ct_warp_affine_normalize(L.ptr(src), 1, image.shape[0], image.shape[1], image.shape[1] * 3,
+                                             L.ptr(minv), C.c_void_p(mean.ctypes.data), C.c_void_p(std.ctypes.data),
+                                             L.ptr(out), inp_h, inp_w, L.stream_ptr()), 'ct_warp_affine_normalize')
+    images = torch.cat((out, out.flip(3)), 0) if self.opt.flip_test else out
     calib = np.array(input_meta['calib'], dtype=np.float32) if 'calib' in input_meta \
         else self._get_default_calib(width, height)
     meta = dict(calib=calib, c=c, s=s, height=height, width=width, out_height=out_h, out_width=out_w,
@@ -234,7 +280,10 @@ class Detector(object):
       cell = np.array([(ox0 + ox1) / 2, (oy0 + oy1) / 2], dtype=np.int32)
       inds.append(cell[1] * out_w + cell[0])
     if with_hm:
-      canvas = torch.from_numpy(canvas[np.newaxis]).to(self.opt.device)
+      canvas = canvas[np.newaxis]
+      if self.opt.flip_test:                                 # detector.py:285-286
+        canvas = np.concatenate((canvas, canvas[:, :, :, ::-1]), axis=0)
+      canvas = torch.from_numpy(np.ascontiguousarray(canvas)).to(self.opt.device)
     pre_inds = torch.from_numpy(np.array(inds, np.int64).reshape(1, -1)).to(self.opt.device)
     return canvas, pre_inds
 
@@ -256,26 +305,118 @@ class Detector(object):
     return output
 
   # ------------------------------------------------------------------------------------ hot path
+  def _flip_plan(self, eng):
+    """Which heads Detector._flip_output (detector.py:311-332) averages with the mirrored pass, and how:
+    {head: (perm or None, sign or None)}; every other head keeps its un-flipped pass."""
+    plan = {}
+    dev = eng.device
+    pairs = {}
+    for a, b in getattr(self, 'flip_idx', None) or get_dataset(self.opt.dataset).flip_idx:
+      pairs[a], pairs[b] = b, a
+    for h, t in eng.outputs.items():
+      c = t.shape[1]
+      if h in ('hm', 'wh', 'dep', 'dim'):
+        plan[h] = (None, None)
+      elif h == 'amodel_offset':                              # flipped copy with its x components negated
+        plan[h] = (None, torch.tensor([-1. if i % 2 == 0 else 1. for i in range(c)], dtype=torch.float32, device=dev))
+      elif h == 'hps':                                        # flip_lr_off: mirror, negate x offsets, swap left/right joints
+        perm = [2 * pairs.get(i // 2, i // 2) + (i % 2) for i in range(c)]
+        plan[h] = (torch.tensor(perm, dtype=torch.int32, device=dev),
+                   torch.tensor([-1. if i % 2 == 0 else 1. for i in range(c)], dtype=torch.float32, device=dev))
+      elif h == 'hm_hp':                                      # flip_lr: mirror, swap left/right joints
+        plan[h] = (torch.tensor([pairs.get(i, i) for i in range(c)], dtype=torch.int32, device=dev), None)
+    return plan
+
+  def _flip_output(self, output, plan, merged):
+    """Device form of detector.py:311-332 on the post-activation maps of a (frame, mirrored frame) pair."""
+    res = {}
+    for h, t in output.items():
+      if h in plan:
+        perm, sign = plan[h]
+        L.check(L.lib().ct_flip_merge(L.ptr(t), L.ptr(merged[h]), t.shape[1], t.shape[2], t.shape[3], L.ptr(perm),
+                                      L.ptr(sign), L.stream_ptr()), 'ct_flip_merge')
+        res[h] = merged[h]
+      else:
+        res[h] = t[0:1]
+    return res
+
+  def _process_plan(self, B, H, W, device, has_pre, has_hm):
+    """Everything `process` launches for one input signature, built once: engine plan, flip-merge buffers, decode
+    buffers, and a CUDA graph of the lot (CTB_NO_GRAPH=1 keeps it eager)."""
+    key = (B, H, W, str(device), has_pre, has_hm, bool(self.opt.flip_test))
+    if not hasattr(self, '_graphs'):
+      self._graphs = {}
+    p = self._graphs.get(key)
+    if p is not None and p['eng'] is self.model.engine_for(B, H, W, device):
+      return p
+    eng = self.model.engine_for(B, H, W, device)
+    if not eng.fused_act:
+      eng.set_fused_activations(True)
+    p = {'eng': eng, 'graph': None, 'rec': None, 'ws': None, 'res': None, 'out': None}
+    if self.opt.flip_test:
+      assert B == 2, 'flip_test runs the frame and its mirror image as a batch of 2'
+      p['plan'] = self._flip_plan(eng)
+      p['merged'] = {h: torch.empty((1,) + tuple(eng.outputs[h].shape[1:]), dtype=torch.float32, device=device)
+                     for h in p['plan']}
+    img = eng.in_img
+    pre = eng.in_pre if has_pre else None
+    hm = eng.in_hm if has_hm else None
+
+    def launch():
+      out = dict(eng.forward(img, pre, hm))
+      if self.opt.flip_test:
+        out = self._flip_output(out, p['plan'], p['merged'])
+      if p['ws'] is None:
+        cat = out['hm'].shape[1]
+        J = out['hm_hp'].shape[1] if ('hm_hp' in out and 'hps' in out) else 0
+        p['ws'] = torch.zeros(L.lib().ct_decode_workspace_bytes(out['hm'].shape[0], cat, J, self.opt.K),
+                              dtype=torch.uint8, device=device)
+      res = generic_decode(out, K=self.opt.K, opt=self.opt, records_out=p['rec'], workspace=p['ws'])
+      p['rec'], p['res'], p['out'] = res.records, res, out
+
+    p['launch'] = launch
+    if not int(os.environ.get('CTB_NO_GRAPH', '0')):
+      side = torch.cuda.Stream(device=device)
+      side.wait_stream(torch.cuda.current_stream())
+      with torch.cuda.stream(side):
+        launch(); launch()
+      torch.cuda.current_stream().wait_stream(side)
+      g = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(g):
+        launch()
+      p['graph'] = g
+    self._graphs[key] = p
+    return p
+
   def process(self, images, pre_images=None, pre_hms=None, pre_inds=None, return_time=False):
-    """detector.py:335-354."""
+    """detector.py:335-354: network + _sigmoid_output (+ _flip_output) + generic_decode + D2H.  One CUDA-graph replay
+    (the 87 launches of the DLA-34 plan, the flip merge, the fused decode) and ONE device->host copy."""
     with torch.no_grad():
       torch.cuda.synchronize()
       B, _, H, W = images.shape
-      eng = self.model.engine_for(B, H, W, images.device)
-      if not eng.fused_act:
-        eng.set_fused_activations(True)
-      f = lambda t: None if t is None else t.float().contiguous()
-      output = dict(eng.forward(f(images), f(pre_images), f(pre_hms) if isinstance(pre_hms, torch.Tensor)
-                                else None))
+      has_hm = isinstance(pre_hms, torch.Tensor)
+      p = self._process_plan(B, H, W, images.device, pre_images is not None, has_hm)
+      eng = p['eng']
+      eng.in_img.copy_(images)
+      if pre_images is not None:
+        eng.in_pre.copy_(pre_images)
+      if has_hm:
+        eng.in_hm.copy_(pre_hms)
+      if p['graph'] is not None:
+        p['graph'].replay()
+      else:
+        p['launch']()
+      output = dict(p['out'])
       output.update({'pre_inds': pre_inds})
       torch.cuda.synchronize()
       forward_time = time.time()
-      dets_dev = generic_decode(output, K=self.opt.K, opt=self.opt)
+      dets_dev = p['res']
       rec = dets_dev.records.cpu().numpy()          # the single device->host copy (synchronises)
       dets = {}
-      for k, v in dets_dev.items():
-        if k == 'pre_cts':
-          dets[k] = v.detach().cpu().numpy()
+      if pre_inds is not None:                      # decode.py:173-180
+        Wo = output['hm'].shape[3]
+        dets['pre_cts'] = torch.stack([(pre_inds % Wo).float(), torch.div(pre_inds, Wo, rounding_mode='floor').float()],
+                                      dim=2).cpu().numpy()
       dets.update(_numpy_views(rec, dets_dev))
     if return_time:
       return output, dets, forward_time

@@ -73,6 +73,7 @@ class opts(object):
                           ('velocity_weight', 1)):
       a('--' + flag, type=float, default=default)
     a('--b200_precision', default='bf16', choices=['bf16', 'fp32', 'bf16x3'])
+    a('--b200_device_pre', action='store_true', help='Detector.run: warpAffine + normalise on the GPU (SURVEY 8f-2)')
     self.parser = p
 
   def parse(self, args=''):

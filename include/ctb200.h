@@ -18,6 +18,11 @@
  *                     + generic_decode, utils.py:16-26,52-87 and decode.py:83-182
  *                     (+ _update_kps_with_hm decode.py:11-81 for the pose heads).
  *   ct_render_pre_hm  Detector._get_additional_inputs's gaussian splat, detector.py:254-290.
+ *   ct_track_step     generic_post_process's affine (utils/post_process.py:21-91) + Tracker.step's greedy association
+ *                     (utils/tracker.py:28-138) + the (centre, radius) boxes of _get_additional_inputs for the next
+ *                     frame, per stream, on the device;  ct_render_tracks splats those boxes (image.py:128-154).
+ *   ct_flip_merge     Detector._flip_output, detector.py:311-332 (flip_tensor / flip_lr / flip_lr_off, model/utils.py:28-50).
+ *   ct_warp_affine_normalize   Detector.pre_process's cv2.warpAffine + normalise + HWC->CHW, detector.py:207-226.
  */
 #ifndef CTB200_H_
 #define CTB200_H_
@@ -190,6 +195,53 @@ int ct_decode(const ct_decode_desc* d, void* stream);
  * (detector.py:264-276); the np.maximum splat of image.py:138-154 runs on the device. */
 int ct_render_pre_hm(const float* boxes, int32_t n, float* pre_hm, int32_t B, int32_t H, int32_t W,
                      void* stream);
+
+/* ---- per-stream state on the device ------------------------------------------ */
+/* One track / result row: the fields Tracker.step reads and writes (utils/tracker.py), image coordinates. */
+#define CT_TRK_SCORE 0
+#define CT_TRK_CLASS 1      /* clses + 1 (post_process.py:47) */
+#define CT_TRK_CT 2         /* ct x, y */
+#define CT_TRK_TRACKING 4   /* tracking dx, dy (already in image coordinates) */
+#define CT_TRK_BBOX 6       /* x0, y0, x1, y1 */
+#define CT_TRK_ID 10        /* tracking_id (exact in fp32 below 2^24) */
+#define CT_TRK_AGE 11
+#define CT_TRK_ACTIVE 12
+#define CT_TRK_FLOATS 13
+
+typedef struct {
+  int32_t B, K, F;            /* decode records [B,K,F] (ct_decode), sorted by score */
+  int32_t rec_tracking;       /* float offset of the `tracking` head inside a record, -1 if absent */
+  int32_t max_tracks;         /* T: rows of the per-stream track table (>= K; tracks beyond T are dropped) */
+  float out_thresh;           /* detections with score > out_thresh survive (detector.py:371-377) */
+  float new_thresh;           /* unmatched detections with score > new_thresh start a track (tracker.py:108-113) */
+  float pre_thresh;           /* tracks with score >= pre_thresh and active != 0 are splatted (detector.py:262-263) */
+  int32_t max_age;            /* unmatched tracks coast while age < max_age (tracker.py:115-126) */
+  int32_t inp_h, inp_w;       /* network input size = pre_hm size */
+  const float* records;
+  const float* trans_out_inv; /* [B,6] fp32: output grid -> image, get_affine_transform(c,s,0,(w,h),inv=1).astype(f32) */
+  const double* trans_input;  /* [B,6] fp64: image -> network input (meta['trans_input']); needed when boxes != NULL */
+  float* tracks;              /* in/out [B,T,CT_TRK_FLOATS]: the stream's tracks == the results of this step */
+  int32_t* counts;            /* in/out [B,2]: number of tracks, id_count */
+  float* boxes;               /* out [B,T,5] rows (b, cx, cy, radius, 0) for ct_render_tracks, radius < 0 = skip; or NULL */
+} ct_track_desc;
+
+int64_t ct_track_smem_bytes(int32_t K, int32_t max_tracks);
+int ct_track_step(const ct_track_desc* d, void* stream);
+/* pre_hm (fp32 [B,1,H,W], zeroed here) <- max-splat of boxes [n,5] (rows with radius < 0 skipped); n is the grid size,
+ * so the launch shape does not depend on the data (CUDA-graph capturable). */
+int ct_render_tracks(const float* boxes, int32_t n, float* pre_hm, int32_t B, int32_t H, int32_t W, void* stream);
+
+/* out[c,y,x] = (in2[0,c,y,x] + sign[c] * in2[1,perm[c],y,W-1-x]) / 2;  in2 fp32 [2,C,H,W], out [1,C,H,W];
+ * perm (int32 [C], device) / sign (fp32 [C], device) may be NULL (identity / +1). */
+int ct_flip_merge(const float* in2, float* out, int32_t C, int32_t H, int32_t W, const int32_t* perm,
+                  const float* sign, void* stream);
+
+/* dst fp32 [B,3,out_h,out_w] = ((warpAffine(src) / 255 - mean) / std), src uint8 [B,src_h,src_w,3] (row pitch src_step
+ * bytes), minv fp64 [B,6] = the INVERTED 2x3 map (dst -> src) exactly as cv::warpAffine inverts it; mean/std host fp32[3].
+ * Bilinear in cv2's fixed point (1/32 px, 15-bit weights), zero border. */
+int ct_warp_affine_normalize(const uint8_t* src, int32_t B, int32_t src_h, int32_t src_w, int32_t src_step,
+                             const double* minv, const float* mean, const float* std, float* dst, int32_t out_h,
+                             int32_t out_w, void* stream);
 
 /* ---- misc --------------------------------------------------------------------------- */
 const char* ct_last_error(void);

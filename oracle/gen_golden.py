@@ -136,6 +136,44 @@ def gen_e2e():
     print('e2e', stem, len(data), 'arrays', 'top score %.4f .. %.4f' % (float(dets['scores'][0, 0]), float(dets['scores'][0, -1])))
 
 
+FLIP_CASES = ['coco_pose', 'nuscenes_ddd']
+
+
+def flip_inputs(hw=SMALL_HW):
+  img, pre, hm = wt.synthetic_inputs(1, hw[0], hw[1], seed=77)
+  cat = lambda t: torch.cat((t, t.flip(3)), 0).contiguous()
+  return cat(img), cat(pre), cat(hm)
+
+
+def gen_flip():
+  """--flip_test (detector.py:225-226,285-286,311-332): the (frame, mirrored frame) pair through the reference
+  model, its _sigmoid_output and _flip_output, then generic_decode of the merged maps."""
+  from detector import Detector as RefDetector
+  from dataset.dataset_factory import get_dataset
+  from model.decode import generic_decode
+  data = {}
+  for cfg in FLIP_CASES:
+    opt, model = rh.build_reference_model(cfg, input_hw=SMALL_HW, extra=['--flip_test'])
+    model.load_state_dict(wt.make_state_dict(model.state_dict(), 317))
+    det = object.__new__(RefDetector)
+    det.opt = opt
+    det.flip_idx = get_dataset(opt.dataset).flip_idx
+    img, pre, hm = flip_inputs()
+    with torch.no_grad():
+      out = model(img, pre, hm)[-1]
+      out = det._sigmoid_output(out)
+      out = det._flip_output(out)
+      out['pre_inds'] = None
+      dets = generic_decode({k: (v.clone() if v is not None else None) for k, v in out.items()}, K=50, opt=opt)
+    for k, v in out.items():
+      if v is not None:
+        data['%s.head.%s' % (cfg, k)] = v.numpy()
+    for k, v in dets.items():
+      data['%s.det.%s' % (cfg, k)] = v.numpy()
+  np.savez_compressed(os.path.join(OUT, 'flip_cases.npz'), **data)
+  print('flip', len(data), 'arrays')
+
+
 def gen_decode():
   from model.decode import generic_decode
   data = {}
@@ -286,7 +324,7 @@ def gen_host():
 if __name__ == '__main__':
   os.makedirs(OUT, exist_ok=True)
   torch.manual_seed(0)
-  which = sys.argv[1:] or ['net', 'e2e', 'decode', 'post', 'host', 'opts']
+  which = sys.argv[1:] or ['net', 'e2e', 'decode', 'post', 'host', 'opts', 'flip']
   rh.install()
   if 'net' in which:
     gen_net()
@@ -300,3 +338,5 @@ if __name__ == '__main__':
     gen_host()
   if 'opts' in which:
     gen_opts()
+  if 'flip' in which:
+    gen_flip()

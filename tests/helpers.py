@@ -78,3 +78,24 @@ def host_case_inputs(i, hw):
   tracks[3]['score'] = 0.05
   calib = np.array([[700., 0, hw[1] / 2., 40.], [0, 700., hw[0] / 2., 1.], [0, 0, 1, 0.01]], dtype=np.float32)
   return image, tracks, calib
+
+
+def flip_inputs(hw=(64, 96)):
+  """Must stay identical to oracle/gen_golden.py::flip_inputs (--flip_test goldens)."""
+  img, pre, hm = wt.synthetic_inputs(1, hw[0], hw[1], seed=77)
+  cat = lambda t: torch.cat((t, t.flip(3)), 0).contiguous()
+  return cat(img), cat(pre), cat(hm)
+
+
+def e2e_frame(hw, batch, frame, seed):
+  """Must stay identical to oracle/gen_golden.py::e2e_frame (full-size goldens)."""
+  img, pre, hm = wt.synthetic_inputs(batch, hw[0], hw[1], seed=seed)
+  return img[frame:frame + 1].clone(), pre[frame:frame + 1].clone(), hm[frame:frame + 1].clone()
+
+
+E2E_CASES = {  # file stem -> (cfg, (H, W), batch, frame, seed); mirrors oracle/gen_golden.py::E2E_CASES
+    'e2e_coco_tracking_512': ('coco_tracking', (512, 512), 1, 0, 317),
+    'e2e_coco_tracking_512_b32f0': ('coco_tracking', (512, 512), 32, 0, 4242),
+    'e2e_coco_tracking_512_b32f31': ('coco_tracking', (512, 512), 32, 31, 4242),
+    'e2e_mot_544x960': ('mot', (544, 960), 1, 0, 317),
+    'e2e_coco_pose_512': ('coco_pose', (512, 512), 1, 0, 317)}

@@ -132,6 +132,30 @@ def test_oracle_dcn_matches_torchvision():
   assert (got - ref).abs().max() < 1e-4
 
 
+@pytest.mark.parametrize('cfg', ['coco_pose', 'nuscenes_ddd'])
+def test_oracle_flip_test_matches_reference_golden(cfg, golden_dir):
+  """--flip_test: oracle network on the (frame, mirrored frame) pair + sigmoid_output + flip_output + decode vs the
+  reference's model + _sigmoid_output + _flip_output + generic_decode (detector.py:311-332)."""
+  from helpers import flip_inputs
+  from centertrack_b200.dataset_info import get_dataset
+  g = np.load(os.path.join(golden_dir, 'flip_cases.npz'))
+  opt, model, sd = make_model(cfg)
+  img, pre, hm = flip_inputs()
+  out = co.sigmoid_output(co.DLA34Oracle(sd, opt.heads).forward(img, pre, hm))
+  merged = co.flip_output(out, get_dataset(opt.dataset).flip_idx)
+  for h in opt.heads:
+    ref = g['%s.head.%s' % (cfg, h)]
+    assert merged[h].shape == ref.shape
+    tol = 1e-3 if h != 'dep' else 2e-2
+    assert np.abs(merged[h] - ref).max() <= tol * max(1.0, np.abs(ref).max()), h
+  # decode of the reference's own merged maps: bit-exact indices
+  od = co.generic_decode({h: g['%s.head.%s' % (cfg, h)] for h in opt.heads}, 50)
+  pos = g[cfg + '.det.scores'][0] > 0          # fewer than K positive peaks on this tiny map: zero-score ties (hazard H1)
+  assert pos.sum() >= 10
+  assert np.array_equal(od['_inds'][0][pos], (g[cfg + '.det.ys'] * 24 + g[cfg + '.det.xs']).astype(np.int64)[0][pos])
+  assert np.array_equal(od['scores'], g[cfg + '.det.scores'])
+
+
 def test_oracle_topk_tie_rule():
   v = np.array([[0.5, 0.0, 0.5, 0.7, 0.0, 0.0]], dtype=np.float32)
   s, i = co.topk_desc(v, 4)
