@@ -313,11 +313,13 @@ def test_full_size_configs_bf16_engine_vs_emulating_oracle(cfg, hw):
 
 
 # ---- what bf16 costs, as hard bounds against the REFERENCE's fp32 outputs (tests/golden/e2e_*.npz) ----------------
-# Errors are |d| / max(1, |ref|max) per tensor (tests/parity.py).  The bounds are ~2x what the oracle predicts for
-# this engine's rounding points (bf16 operands and activation storage, fp32 accumulate: 50 layers x ~3e-3 each on a
-# network of unit perturbation gain -> ~3e-2 at the heads); the fp32 engine meets north_star's 1e-3 on the same files.
-BF16_BOUNDS = {'head_max': 0.2, 'stage_max': 0.2, 'bbox_max': 0.8, 'tracking_max': 0.6, 'topk_overlap': 0.6}
-BF16_SCORE_MAX = {'coco_tracking': 0.05, 'mot': 0.25, 'coco_pose': 0.25}
+# Errors are |d| / max(1, |ref|max) per tensor (tests/parity.py).  The bounds are ~1.5x what was measured on the B200
+# (round 2: head max 0.070-0.100, stage max 0.063-0.097, |d score| at reference peaks 0.014-0.083, |d bbox| 0.24-0.41
+# output px, |d tracking| 0.23-0.33 px, top-100 overlap 0.75-0.84) -- which is what the oracle predicts for this
+# engine's rounding points (bf16 operands and activation storage, fp32 accumulate: 50 layers x ~3e-3 each on a network
+# of unit perturbation gain -> ~3e-2 rms at the heads).  The fp32 engine measures 1.2e-5 on the same files.
+BF16_BOUNDS = {'head_max': 0.15, 'stage_max': 0.15, 'bbox_max': 0.7, 'tracking_max': 0.55, 'topk_overlap': 0.65}
+BF16_SCORE_MAX = {'coco_tracking': 0.05, 'mot': 0.15, 'coco_pose': 0.1}
 
 
 def _dump(name, obj):
