@@ -186,7 +186,8 @@ def _op_group(kind, pl, L):
     return kind
   if pl.a_mode == L.CT_A_DCN:
     return 'dcn_main'
-  return {L.CT_ENGINE_TCGEN05: 'conv_tc', L.CT_ENGINE_TCGEN05_HALO: 'conv_halo', L.CT_ENGINE_SIMT: 'conv_simt'}[pl.engine]
+  return {L.CT_ENGINE_TCGEN05: 'conv_tc', L.CT_ENGINE_TCGEN05_HALO: 'conv_halo', L.CT_ENGINE_SIMT: 'conv_simt',
+          L.CT_ENGINE_TCGEN05_X3: 'conv_tc'}[pl.engine]
 
 
 def per_op_times(runner, L, reps=5):
@@ -477,6 +478,8 @@ def main():
       'peak_source': peak_src, 'method': method,
       'kernels': {'dcn_main': dcn, 'conv_tc_plain': tc, 'conv_halo': halo, 'conv_simt': simt},
       'ms_by_group': {k: round(v['ms'], 4) for k, v in groups.items()},
+      'top_ops_us': [[n, round(t * 1000, 1)] for t, n in sorted(((dt, name) for (kind, pl, name), dt in zip(eng.ops, op_ms)),
+                                                             reverse=True)[:24]],
       'sum_kernel_ms': round(raw_sum, 4), 'ms_per_step': round(ms_per_step, 4),
       'sum_over_step': raw_sum / ms_per_step, 'rescaled_to_step': rescaled,
       'decode': {'us_per_launch': round(decode_ms * 1000, 1), 'frames': B, 'bound': 'hbm', 'achieved': dec_gbs,

@@ -17,7 +17,7 @@ CT_F32, CT_BF16 = 0, 1
 CT_A_CONV, CT_A_DCN = 0, 1
 CT_OUT_NHWC, CT_OUT_NHWC_F32, CT_OUT_NCHW_F32 = 0, 1, 2
 CT_HEAD_NONE, CT_HEAD_SIGMOID, CT_HEAD_DEPTH = 0, 1, 2
-CT_ENGINE_SIMT, CT_ENGINE_TCGEN05, CT_ENGINE_TCGEN05_HALO = 0, 1, 2
+CT_ENGINE_SIMT, CT_ENGINE_TCGEN05, CT_ENGINE_TCGEN05_HALO, CT_ENGINE_TCGEN05_X3 = 0, 1, 2, 3
 CT_ROLE_RAW, CT_ROLE_REG, CT_ROLE_WH, CT_ROLE_LTRB, CT_ROLE_LTRB_AMODAL, CT_ROLE_HPS = range(6)
 CT_DECODE_MAX_HEADS = 12
 CT_REC_SCORE, CT_REC_CLS, CT_REC_XS, CT_REC_YS, CT_REC_BBOX, CT_REC_IND, CT_REC_HEADS = 0, 1, 2, 3, 4, 8, 9
@@ -70,7 +70,7 @@ class TrackDesc(C.Structure):
 
 
 EXPORTS = ['ct_packed_weight_bytes', 'ct_pack_weights', 'ct_conv_forward', 'ct_stem_forward',
-           'ct_pack_stem_input', 'ct_maxpool2', 'ct_upsample_add', 'ct_decode_workspace_bytes', 'ct_decode',
+           'ct_pack_stem_input', 'ct_pack_stem_input_f32', 'ct_maxpool2', 'ct_upsample_add', 'ct_decode_workspace_bytes', 'ct_decode',
            'ct_render_pre_hm', 'ct_track_smem_bytes', 'ct_track_step', 'ct_render_tracks', 'ct_flip_merge',
            'ct_warp_affine_normalize', 'ct_last_error', 'ct_abi_version', 'ct_launch_count',
            'ct_reset_launch_count', 'ct_debug_trace', 'ct_debug_watch']
@@ -116,6 +116,7 @@ def lib():
   L.ct_conv_forward.argtypes = [C.POINTER(ConvDesc), C.c_void_p]
   L.ct_stem_forward.argtypes = [C.c_void_p] * 6 + [C.c_int32] * 5 + [C.c_void_p]
   L.ct_pack_stem_input.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p]
+  L.ct_pack_stem_input_f32.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p]
   L.ct_maxpool2.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p]
   L.ct_upsample_add.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 9 + [C.c_void_p]
   L.ct_decode_workspace_bytes.restype = C.c_int64

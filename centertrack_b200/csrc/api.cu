@@ -42,7 +42,7 @@ extern "C" int64_t ct_packed_weight_bytes(int32_t engine, int32_t C_out, int32_t
     if (!(C_in == 8 || (C_in % 16 == 0 && C_in <= 64) || (C_in % 64 == 0 && C_in <= 256))) return -1;
     return n_tiles * halo_blocks(C_in, KH, KW) * (int64_t)n_tile * 32;
   }
-  return n_tiles * tc_k_slices(C_in, KH, KW) * (int64_t)n_tile * 64 * 2;
+  return n_tiles * tc_k_slices(C_in, KH, KW) * (int64_t)n_tile * 64 * 2 * (engine == CT_ENGINE_TCGEN05_X3 ? 2 : 1);
 }
 
 extern "C" int ct_pack_weights(int32_t engine, const float* w, int32_t C_out, int32_t C_in, int32_t KH,
@@ -85,8 +85,9 @@ extern "C" int ct_pack_weights(int32_t engine, const float* w, int32_t C_out, in
   }
   const int ks = tc_k_slices(C_in, KH, KW);
   const int n_tiles = (C_out + n_tile - 1) / n_tile;
+  const int parts = engine == CT_ENGINE_TCGEN05_X3 ? 2 : 1;     // x3: [hi tile][lo tile] per K slice
   uint16_t* o = (uint16_t*)dst;
-  memset(o, 0, (size_t)n_tiles * ks * n_tile * 64 * 2);
+  memset(o, 0, (size_t)n_tiles * ks * n_tile * 64 * 2 * parts);
   for (int oc = 0; oc < C_out; ++oc) {
     const int nt = oc / n_tile, r = oc % n_tile;
     for (int t = 0; t < taps; ++t)
@@ -94,8 +95,16 @@ extern "C" int ct_pack_weights(int32_t engine, const float* w, int32_t C_out, in
         const int k = t * C_in + c;
         const int s = k / 64, j = k % 64;
         const int chunk = (j / 8) ^ (r & 7);           // 128B swizzle: 16B chunk index XOR row%8
-        const size_t off = ((size_t)nt * ks + s) * n_tile * 64 + (size_t)r * 64 + chunk * 8 + (j % 8);
-        o[off] = f32_to_bf16_rn(w[((size_t)oc * C_in + c) * taps + t]);
+        const size_t off = ((size_t)nt * ks + s) * n_tile * 64 * parts + (size_t)r * 64 + chunk * 8 + (j % 8);
+        const float wv = w[((size_t)oc * C_in + c) * taps + t];
+        const uint16_t hi = f32_to_bf16_rn(wv);
+        o[off] = hi;
+        if (parts == 2) {
+          uint32_t hu = (uint32_t)hi << 16;
+          float hf;
+          memcpy(&hf, &hu, 4);
+          o[off + (size_t)n_tile * 64] = f32_to_bf16_rn(wv - hf);
+        }
       }
   }
   return CT_OK;
@@ -120,6 +129,10 @@ extern "C" int ct_conv_forward(const ct_conv_desc* d, void* stream) {
   if (d->engine == CT_ENGINE_SIMT) return conv_forward_simt(d, st);
   if (d->engine == CT_ENGINE_TCGEN05) {
     CT_REQUIRE(d->dtype == CT_BF16, "tcgen05 engine needs bf16 activations");
+    return conv_forward_tc(d, st);
+  }
+  if (d->engine == CT_ENGINE_TCGEN05_X3) {
+    CT_REQUIRE(d->dtype == CT_F32, "tcgen05 x3 engine runs on fp32 activations");
     return conv_forward_tc(d, st);
   }
   if (d->engine == CT_ENGINE_TCGEN05_HALO) {

@@ -32,8 +32,8 @@ constexpr int A_STAGE_BYTES = TC_BM * 128;
 
 struct TcArgs {
   ConvGeom g;
-  const __nv_bfloat16* x;
-  const __nv_bfloat16* w;       // packed tiles
+  const __nv_bfloat16* x;       // X3 engine: fp32 activations behind the same pointers (xf() / residual_f())
+  const __nv_bfloat16* w;       // packed tiles (X3: [hi tile][lo tile] per K slice)
   const float* shift;
   const __nv_bfloat16* residual;
   const float* om;
@@ -185,7 +185,31 @@ __device__ __forceinline__ uint4 pack8(const unsigned long long (&acc)[4]) {
   return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 2)
+// ---- bf16x3 ("X3") engine: fp32 activations, every operand split into bf16 hi + bf16 lo = x - hi (both exact in
+// fp32), and D += A_hi B_hi + A_hi B_lo + A_lo B_hi on the tensor cores with fp32 accumulation: the dropped
+// A_lo B_lo term and the rounding of lo are ~2^-16 / 2^-17 relative, i.e. ~1e-5 per layer instead of bf16's 4e-3.
+__device__ __forceinline__ void split8(const float4 lo4, const float4 hi4, uint4& h, uint4& l) {
+  const float f[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+  uint32_t hh[4], ll[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const __nv_bfloat162 hp = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+    const float2 hf = __bfloat1622float2(hp);
+    const __nv_bfloat162 lp = __floats2bfloat162_rn(f[2 * q] - hf.x, f[2 * q + 1] - hf.y);
+    hh[q] = *reinterpret_cast<const uint32_t*>(&hp);
+    ll[q] = *reinterpret_cast<const uint32_t*>(&lp);
+  }
+  h = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+  l = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+}
+__device__ __forceinline__ float4 ldg_nc_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+template <bool X3>
+__global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2)
 conv_tc_kernel(const TcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   // SWIZZLE_128B operands need 1024B-aligned stage bases: align by hand (launch adds 1 KB of slack)
@@ -193,13 +217,16 @@ conv_tc_kernel(const TcArgs a) {
   const ConvGeom& g = a.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = a.stages;
-  const uint32_t b_stage_bytes = (uint32_t)a.n_tile * 128u;
+  const uint32_t b_tile_bytes = (uint32_t)a.n_tile * 128u;                    // one bf16 weight tile of a K slice
+  const uint32_t b_stage_bytes = X3 ? 2u * b_tile_bytes : b_tile_bytes;       // X3: [hi][lo]
+  constexpr uint32_t a_stage_bytes = X3 ? 2u * A_STAGE_BYTES : A_STAGE_BYTES; // X3: [hi 16 KB][lo 16 KB]
+  const float* xf = reinterpret_cast<const float*>(a.x);
 
   // carve shared memory
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t sA = smem_base;
-  const uint32_t sB = sA + S * A_STAGE_BYTES;
-  const uint32_t off_bar = S * A_STAGE_BYTES + S * b_stage_bytes;
+  const uint32_t sB = sA + S * a_stage_bytes;
+  const uint32_t off_bar = S * a_stage_bytes + S * b_stage_bytes;
   const uint32_t bars = smem_base + off_bar;           // full[S], empty[S], tmem_full
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + off_bar + (2 * S + 1) * 8);
   DcnEntry* dcn_tab = reinterpret_cast<DcnEntry*>(smem + off_bar + (2 * S + 1) * 8 + 8);  // 16B aligned
@@ -316,9 +343,122 @@ conv_tc_kernel(const TcArgs a) {
     }
     const int cin8 = g.C_in >> 3;
     const int ntaps = g.KH * g.KW;
-    const __nv_bfloat16* wt = a.w + (size_t)nt * a.k_slices * a.n_tile * TC_BK;
+    const size_t w_slice_elems = (size_t)(X3 ? 2 : 1) * a.n_tile * TC_BK;
+    const __nv_bfloat16* wt = a.w + (size_t)nt * a.k_slices * w_slice_elems;
 
-    if (a.a_mode == CT_A_DCN) {
+    if constexpr (X3) {
+      // ---- bf16x3 producers: fp32 activations, each 8-channel chunk = two 16-byte loads, split into hi / lo tiles
+      auto begin_stage = [&](int s) {
+        const int stage = s % S;
+        const uint32_t ph = (uint32_t)(s / S) & 1u;
+        mbar_wait(empty_bar(stage), ph ^ 1u);
+        if (tid == 0) {
+          mbar_expect_tx(full_bar(stage), b_stage_bytes);
+          bulk_g2s(sB + stage * b_stage_bytes, wt + (size_t)s * w_slice_elems, b_stage_bytes, full_bar(stage));
+        }
+        return stage;
+      };
+      auto end_stage = [&](int s, int stage) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar(stage));
+        if (tid == 0) tc_stamp(8 + s);
+      };
+      if (a.a_mode == CT_A_DCN) {
+        float4 va[2][4][2], vb[2][4][2];
+        auto load_half = [&](int tap, int c, int half, float4 (&v)[2][4][2]) {
+          const DcnEntry* tab = dcn_tab + (tap < ntaps ? tap : 0) * TC_BM + r0 + 64 * half;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int4 o = *reinterpret_cast<const int4*>(&tab[32 * j]);     // off, dxo, dyo
+            const float* p00 = xf + (o.x + c);
+            v[j][0][0] = ldg_nc_f4(p00);             v[j][0][1] = ldg_nc_f4(p00 + 4);
+            v[j][1][0] = ldg_nc_f4(p00 + o.y);       v[j][1][1] = ldg_nc_f4(p00 + o.y + 4);
+            v[j][2][0] = ldg_nc_f4(p00 + o.z);       v[j][2][1] = ldg_nc_f4(p00 + o.z + 4);
+            v[j][3][0] = ldg_nc_f4(p00 + o.z + o.y); v[j][3][1] = ldg_nc_f4(p00 + o.z + o.y + 4);
+          }
+        };
+        auto blend_half = [&](int tap, int stage, int half, const float4 (&v)[2][4][2]) {
+          const bool live = tap < ntaps;
+          const DcnEntry* tab = dcn_tab + (live ? tap : 0) * TC_BM + r0 + 64 * half;
+          const uint32_t dst = sA + stage * a_stage_bytes + (uint32_t)(r0 + 64 * half) * 128u + swz;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const float4 w = *reinterpret_cast<const float4*>(&tab[32 * j].w00);
+            const float ww[4] = {w.x, w.y, w.z, w.w};
+            float4 acc[2];
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              acc[h2] = make_float4(ww[0] * v[j][0][h2].x, ww[0] * v[j][0][h2].y, ww[0] * v[j][0][h2].z, ww[0] * v[j][0][h2].w);
+#pragma unroll
+              for (int cn = 1; cn < 4; ++cn) {
+                acc[h2].x = fmaf(ww[cn], v[j][cn][h2].x, acc[h2].x); acc[h2].y = fmaf(ww[cn], v[j][cn][h2].y, acc[h2].y);
+                acc[h2].z = fmaf(ww[cn], v[j][cn][h2].z, acc[h2].z); acc[h2].w = fmaf(ww[cn], v[j][cn][h2].w, acc[h2].w);
+              }
+            }
+            uint4 hi, lo;
+            split8(acc[0], acc[1], hi, lo);
+            if (!live) { hi = make_uint4(0, 0, 0, 0); lo = hi; }
+            sts16(dst + j * 4096u, hi);
+            sts16(dst + A_STAGE_BYTES + j * 4096u, lo);
+          }
+        };
+        int tap = q / cin8, cq = q - tap * cin8;
+        load_half(tap, cq << 3, 0, va);
+        for (int s = 0; s < a.k_slices; ++s) {
+          load_half(tap, cq << 3, 1, vb);
+          const int stage = begin_stage(s);
+          blend_half(tap, stage, 0, va);
+          int ntap = tap, ncq = cq + 8;
+          while (ncq >= cin8) { ncq -= cin8; ++ntap; }
+          if (s + 1 < a.k_slices) load_half(ntap, ncq << 3, 0, va);
+          blend_half(tap, stage, 1, vb);
+          tap = ntap; cq = ncq;
+          end_stage(s, stage);
+        }
+      } else {
+        int ltap = q / cin8, lcq = q - ltap * cin8;
+        auto load_slice = [&](bool in_range, float4 (&v)[TC_NROW][2]) {
+#pragma unroll
+          for (int i = 0; i < TC_NROW; ++i) { v[i][0] = make_float4(0.f, 0.f, 0.f, 0.f); v[i][1] = v[i][0]; }
+          if (in_range && ltap < ntaps) {
+            const int ky = ltap / g.KW, kx = ltap - ky * g.KW;
+            const int tap_off = (ky * g.W + kx) * g.ld_in + (lcq << 3);
+#pragma unroll
+            for (int i = 0; i < TC_NROW; ++i)
+              if ((unsigned)(row_iy[i] + ky) < (unsigned)g.H && (unsigned)(row_ix[i] + kx) < (unsigned)g.W) {
+                const float* pp = xf + (row_off[i] + tap_off);
+                v[i][0] = ldg_nc_f4(pp); v[i][1] = ldg_nc_f4(pp + 4);
+              }
+          }
+          lcq += 8;
+          while (lcq >= cin8) { lcq -= cin8; ++ltap; }
+        };
+        auto store_slice = [&](int s, const float4 (&v)[TC_NROW][2]) {
+          const int stage = begin_stage(s);
+          const uint32_t dst = sA + stage * a_stage_bytes + (uint32_t)r0 * 128u + swz;
+#pragma unroll
+          for (int i = 0; i < TC_NROW; ++i) {
+            uint4 hi, lo;
+            split8(v[i][0], v[i][1], hi, lo);
+            sts16(dst + i * 4096u, hi);
+            sts16(dst + A_STAGE_BYTES + i * 4096u, lo);
+          }
+          end_stage(s, stage);
+        };
+        const int KS = a.k_slices;
+        float4 v0[TC_NROW][2], v1[TC_NROW][2], v2[TC_NROW][2];
+        load_slice(0 < KS, v0);
+        load_slice(1 < KS, v1);
+        load_slice(2 < KS, v2);
+        for (int s = 0; s < KS; s += 3) {
+          store_slice(s, v0);
+          load_slice(s + 3 < KS, v0);
+          if (s + 1 < KS) { store_slice(s + 1, v1); load_slice(s + 4 < KS, v1); }
+          if (s + 2 < KS) { store_slice(s + 2, v2); load_slice(s + 5 < KS, v2); }
+        }
+      }
+    } else if (a.a_mode == CT_A_DCN) {
       // Software-pipelined by half slices (2 of the thread's 4 rows): the 8 corner loads of the next half are in
       // flight while the current half is blended (the gather is latency-bound -- memory-level parallelism first --
       // and the blend is issue-bound: packed FFMA2, one-op bf16 unpack).  A slice whose tap index runs past the
@@ -453,7 +593,23 @@ conv_tc_kernel(const TcArgs a) {
           for (int j = 0; j < 16; ++j) if (o0 + j < g.C_out) v[j] += __ldg(a.shift + o0 + j);
         }
       }
-      if (g.out_mode == CT_OUT_NHWC) {
+      if (X3 && g.out_mode == CT_OUT_NHWC) {            // fp32 activations in, fp32 activations out
+        if (a.residual) {
+          const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.residual) + (size_t)p * g.ld_res + o0);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 rr = ldg_nc_f4(reinterpret_cast<const float*>(rp + j4));
+            v[4 * j4] += rr.x; v[4 * j4 + 1] += rr.y; v[4 * j4 + 2] += rr.z; v[4 * j4 + 3] += rr.w;
+          }
+        }
+        if (g.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + (size_t)p * g.ld_out + o0);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) op[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+      } else if (g.out_mode == CT_OUT_NHWC) {
         if (a.residual) {
           const uint4* rp = reinterpret_cast<const uint4*>(a.residual + (size_t)p * g.ld_res + o0);
           const uint4 ra = ldg_nc16(rp), rb = ldg_nc16(rp + 1);
@@ -522,11 +678,22 @@ conv_tc_kernel(const TcArgs a) {
       const uint32_t ph = (uint32_t)(s / S) & 1u;
       mbar_wait(full_bar(stage), ph);
       tc_fence_after();
-      const uint64_t ad = make_sdesc(sA + stage * A_STAGE_BYTES);
+      const uint64_t ad = make_sdesc(sA + stage * a_stage_bytes);
       const uint64_t bd = make_sdesc(sB + stage * b_stage_bytes);
+      if constexpr (X3) {
+        const uint64_t ad_lo = make_sdesc(sA + stage * a_stage_bytes + A_STAGE_BYTES);
+        const uint64_t bd_lo = make_sdesc(sB + stage * b_stage_bytes + b_tile_bytes);
 #pragma unroll
-      for (int k = 0; k < TC_BK / 16; ++k)
-        tc_mma(tmem_base, ad + 2ull * k, bd + 2ull * k, idesc, (s > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < TC_BK / 16; ++k) {      // small cross terms first, then the hi x hi term
+          tc_mma(tmem_base, ad_lo + 2ull * k, bd + 2ull * k, idesc, (s > 0 || k > 0) ? 1u : 0u);
+          tc_mma(tmem_base, ad + 2ull * k, bd_lo + 2ull * k, idesc, 1u);
+          tc_mma(tmem_base, ad + 2ull * k, bd + 2ull * k, idesc, 1u);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k)
+          tc_mma(tmem_base, ad + 2ull * k, bd + 2ull * k, idesc, (s > 0 || k > 0) ? 1u : 0u);
+      }
       tc_commit(empty_bar(stage));     // frees this smem stage when the MMAs above have read it
     }
     tc_commit(tmem_full_bar);           // accumulator complete -> epilogue
@@ -549,6 +716,7 @@ int tc_set_trace(void* buf) {
 }
 
 int conv_forward_tc(const ct_conv_desc* d, cudaStream_t st) {
+  const bool x3 = d->engine == CT_ENGINE_TCGEN05_X3;     // fp32 activations, bf16 hi/lo split operands
   TcArgs a;
   a.g = make_geom(d);
   const ConvGeom& g = a.g;
@@ -561,7 +729,7 @@ int conv_forward_tc(const ct_conv_desc* d, cudaStream_t st) {
     return fail(CT_ERR_INVALID, "conv_tc: n_tile must be a multiple of 16 in [16,256]%s (%ld)", "", n_tile);
   if (g.out_mode == CT_OUT_NHWC) {
     if (g.C_out % 16 != 0 || g.ld_out % 8 != 0)
-      return fail(CT_ERR_INVALID, "conv_tc: NHWC bf16 output needs C_out %% 16 == 0 and ld_out %% 8 == 0%s", "");
+      return fail(CT_ERR_INVALID, "conv_tc: NHWC output needs C_out %% 16 == 0 and ld_out %% 8 == 0%s", "");
     if (d->residual && (g.ld_res % 8 != 0 || ((uintptr_t)d->residual & 15)))
       return fail(CT_ERR_INVALID, "conv_tc: residual must be 16B aligned with ld_res %% 8 == 0%s", "");
   } else if (g.out_mode == CT_OUT_NHWC_F32) {
@@ -583,8 +751,9 @@ int conv_forward_tc(const ct_conv_desc* d, cudaStream_t st) {
   int cols = 32;
   while (cols < n_tile) cols <<= 1;
   a.tmem_cols = cols;
+  const size_t stage_bytes = (size_t)(x3 ? 2 : 1) * (A_STAGE_BYTES + n_tile * 128);
   auto smem_for = [&](int stg) {
-    return (size_t)stg * (A_STAGE_BYTES + n_tile * 128) + (2 * stg + 1) * 8 + 16 +
+    return (size_t)stg * stage_bytes + (2 * stg + 1) * 8 + 16 +
            (d->a_mode == CT_A_DCN ? 9 * TC_BM * sizeof(DcnEntry) : 0) + 1024;
   };
   int stages = 4;                                   // keep >= 2 CTAs per SM when the tile allows it
@@ -595,6 +764,13 @@ int conv_forward_tc(const ct_conv_desc* d, cudaStream_t st) {
     static const int dcn_stages = getenv("CTB_TC_DCN_STAGES") ? atoi(getenv("CTB_TC_DCN_STAGES")) : 2;
     if (dcn_stages >= 2 && dcn_stages < stages) stages = dcn_stages;
   }
+  if (x3) {                                         // one CTA per SM (register-heavy producers): as deep as fits
+    stages = 4;
+    while (stages > 2 && smem_for(stages) > 200 * 1024) --stages;
+    if (d->a_mode == CT_A_DCN && stages > 3) stages = 3;
+    if (smem_for(stages) > 224 * 1024)
+      return fail(CT_ERR_UNSUPPORTED, "conv_tc x3: tile does not fit in shared memory%s (%ld)", "", (long)n_tile);
+  }
   if (stages > a.k_slices) stages = a.k_slices;
   a.stages = stages;
   const size_t smem = smem_for(stages);
@@ -603,7 +779,8 @@ int conv_forward_tc(const ct_conv_desc* d, cudaStream_t st) {
     cudaGetDevice(&dev);
     static thread_local unsigned long long attr_set_mask = 0;      // the attribute is per device
     if (dev >= 64 || !((attr_set_mask >> dev) & 1ull)) {
-      CT_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+      CT_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+      CT_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
       if (dev < 64) attr_set_mask |= 1ull << dev;
     }
   }
@@ -619,7 +796,8 @@ int conv_forward_tc(const ct_conv_desc* d, cudaStream_t st) {
     m_tiles = g.B * a.tiles_x * a.tiles_y;
   }
   dim3 grid(m_tiles, n_tiles);
-  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(a);
+  if (x3) conv_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(a);
+  else conv_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(a);
   return after_launch();
 }
 

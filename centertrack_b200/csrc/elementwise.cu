@@ -94,6 +94,25 @@ __global__ void pack_stem_kernel(const float* __restrict__ img, const float* __r
   }
 }
 
+// fp32 variant for the bf16x3 engine: fp32 NCHW x3 -> fp32 NHWC [.,8]
+__global__ void pack_stem_f32_kernel(const float* __restrict__ img, const float* __restrict__ pre,
+                                     const float* __restrict__ hm, float4* __restrict__ out, int B, int H, int W) {
+  const size_t plane = (size_t)H * W, total = (size_t)B * plane;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / plane, r = i - b * plane;
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      v[c] = __ldg(img + (b * 3 + c) * plane + r);
+      v[3 + c] = pre ? __ldg(pre + (b * 3 + c) * plane + r) : 0.f;
+    }
+    v[6] = hm ? __ldg(hm + b * plane + r) : 0.f;
+    v[7] = 0.f;
+    out[2 * i] = make_float4(v[0], v[1], v[2], v[3]);
+    out[2 * i + 1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Tree.downsample: 2x2 max-pool, 16-byte vectors (8 bf16 / 4 fp32 channels per thread), output may be a channel
 // slice of a concat buffer (ld_out)
@@ -318,6 +337,15 @@ extern "C" int ct_pack_stem_input(const float* img, const float* pre_img, const 
   CT_REQUIRE(B > 0 && H > 0 && W > 0, "bad shape");
   const size_t total = (size_t)B * H * W;
   pack_stem_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(img, pre_img, pre_hm, (uint4*)out, B, H, W);
+  return after_launch();
+}
+
+extern "C" int ct_pack_stem_input_f32(const float* img, const float* pre_img, const float* pre_hm, float* out,
+                                      int32_t B, int32_t H, int32_t W, void* stream) {
+  CT_REQUIRE(img && out, "null pointer");
+  CT_REQUIRE(B > 0 && H > 0 && W > 0, "bad shape");
+  const size_t total = (size_t)B * H * W;
+  pack_stem_f32_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(img, pre_img, pre_hm, (float4*)out, B, H, W);
   return after_launch();
 }
 

@@ -15,8 +15,10 @@ on NHWC activations:
     1x1 per head writing the reference-layout fp32 NCHW map (sigmoid / depth transform of
     detector.py:300-308 optionally fused).
 
-precision='bf16' : bf16 activations, tcgen05 engine (fast path)
-precision='fp32' : fp32 activations, SIMT engine (reference-accuracy path, <= 1e-3 of the reference)
+precision='bf16'   : bf16 activations, tcgen05 engines (fast path)
+precision='bf16x3' : fp32 activations, tcgen05 gather engine with bf16 hi/lo split operands (three MMAs per product
+                     term, fp32 accumulate): the tensor-core path that stays within 1e-3 of the reference
+precision='fp32'   : fp32 activations, SIMT engine (reference-accuracy path, <= 1e-3 of the reference)
 """
 import ctypes as C
 
@@ -54,7 +56,7 @@ class DLA34Engine(object):
 
   def __init__(self, state_dict, heads, B, H, W, precision='bf16', device='cuda',
                depth_scale=1.0, has_pre_img=True, has_pre_hm=True, use_halo=True, dla_node='dcn'):
-    assert precision in ('bf16', 'fp32')
+    assert precision in ('bf16', 'fp32', 'bf16x3')
     assert dla_node in ('dcn', 'conv', 'gcn')
     self.dla_node = dla_node
     assert H % 32 == 0 and W % 32 == 0, 'DLA-34 needs input sizes divisible by 32'
@@ -67,7 +69,8 @@ class DLA34Engine(object):
     self.device = torch.device(device)
     self.dtype = torch.bfloat16 if precision == 'bf16' else torch.float32
     self.ct_dtype = L.CT_BF16 if precision == 'bf16' else L.CT_F32
-    self.engine = L.CT_ENGINE_TCGEN05 if precision == 'bf16' else L.CT_ENGINE_SIMT
+    self.engine = {'bf16': L.CT_ENGINE_TCGEN05, 'fp32': L.CT_ENGINE_SIMT, 'bf16x3': L.CT_ENGINE_TCGEN05_X3}[precision]
+    self.x3 = (precision == "bf16x3")
     self.depth_scale = float(depth_scale)
     self.has_pre_img = has_pre_img and ('base.pre_img_layer.0.weight' in self.sd)
     self.has_pre_hm = has_pre_hm and ('base.pre_hm_layer.0.weight' in self.sd)
@@ -140,7 +143,9 @@ class DLA34Engine(object):
     OW = (x.W + 2 * pad_w - kw) // stride + 1
     P = self.B * OH * OW
     engine = self.engine
-    n_tile = self._pick_n_tile(P, C_out) if engine == L.CT_ENGINE_TCGEN05 else 0
+    n_tile = self._pick_n_tile(P, C_out) if engine in (L.CT_ENGINE_TCGEN05, L.CT_ENGINE_TCGEN05_X3) else 0
+    if engine == L.CT_ENGINE_TCGEN05_X3 and n_tile > 128 and a_mode == L.CT_A_DCN:
+      n_tile = 128            # x3 DCN: two 36 KB-table stages of (32 + 2 x n_tile/8) KB must fit
     if engine == L.CT_ENGINE_TCGEN05 and self.use_halo and a_mode == L.CT_A_CONV and stride == 1 and kh == kw and \
         (C_in in (16, 32, 48, 64, 128, 192, 256) or (C_in == 8 and sum3)):
       k = kh
@@ -280,13 +285,38 @@ class DLA34Engine(object):
       for si, (c0, cn) in enumerate(((0, 3), (3, 3), (6, 1))):
         w48[16 * si:16 * si + 16, c0:c0 + cn] = wst[:, c0:c0 + cn, :].reshape(7, 7, cn, 16).permute(3, 2, 0, 1)
       self.stem_desc = self._conv('stem', x8, w48, shst.reshape(48), x0, 7, 1, relu=False, sum3=7)
+    elif self.x3:
+      # bf16x3 stem: pack (img, pre, hm) -> fp32 NHWC [.,8], one 7x7 conv 8 -> 48 (block-diagonal over the three stems)
+      # with shift + ReLU per stem; the sum of the three (dla.py:307-311) is folded into level0, whose 3x3 conv reads
+      # the 48 channels with its weights tiled three times along the input (conv(a + b + c) = conv over [a|b|c])
+      x8 = TV(self._buf(H, W, 8), 0, 8)
+      self.ops.append(('pack32', x8, 'stem.pack'))
+      w48 = torch.zeros((48, 8, 7, 7), dtype=torch.float64)
+      sh48 = shst.clone()
+      for si, (c0, cn) in enumerate(((0, 3), (3, 3), (6, 1))):
+        w48[16 * si:16 * si + 16, c0:c0 + cn] = wst[:, c0:c0 + cn, :].reshape(7, 7, cn, 16).permute(3, 2, 0, 1)
+      x0 = TV(self._buf(H, W, 48), 0, 48)
+      self.stem48 = self._conv('stem48', x8, w48, sh48.reshape(48), x0, 7, 1, relu=True)
+      # an absent input (pre_img / pre_hm is None, dla.py:308-311) must contribute nothing: its packed channels are
+      # zero, so only its group's shift has to go -> one shift vector per presence mask
+      self.stem48_shift = {}
+      for mask in range(8):
+        shm = sh48.clone()
+        for gi in range(3):
+          if not (mask >> gi) & 1:
+            shm[gi] = 0
+        self.stem48_shift[mask] = self._dev(shm.reshape(48).to(f32).contiguous())
     else:
       self.ops.append(('stem', x0, 'stem'))
     self.named['stem'] = x0
 
     # ---- level0 / level1 ----
     l0 = TV(self._buf(H, W, 16), 0, 16)
-    self._conv_bn('base.level0', x0, 'base.level0.0', 'base.level0.1', l0, 3, 1)
+    if self.x3:
+      w0, sh0 = self._fold('base.level0.0', 'base.level0.1')
+      self._conv('base.level0', x0, w0.repeat(1, 3, 1, 1), sh0, l0, 3, 1)
+    else:
+      self._conv_bn('base.level0', x0, 'base.level0.0', 'base.level0.1', l0, 3, 1)
     l1 = TV(self._buf(H // 2, W // 2, 32), 0, 32)
     self._conv_bn('base.level1', l0, 'base.level1.0', 'base.level1.1', l1, 3, 2)
 
@@ -423,12 +453,16 @@ class DLA34Engine(object):
     if kind == 'conv':
       if pl.epilogue_sum3:          # stem: which of (img, pre_img, pre_hm) exist this call (dla.py:308-311)
         pl.epilogue_sum3 = 1 | (2 if pre_ptr.value else 0) | (4 if hm_ptr.value else 0)
+      elif name == 'stem48':
+        pl.shift = self.stem48_shift[1 | (2 if pre_ptr.value else 0) | (4 if hm_ptr.value else 0)].data_ptr()
       rc = lib.ct_conv_forward(C.byref(pl), st)
     elif kind == 'stem':
       rc = lib.ct_stem_forward(img_ptr, pre_ptr, hm_ptr, L.ptr(self.stem_w), L.ptr(self.stem_shift),
                                C.c_void_p(pl.ptr), self.ct_dtype, self.B, self.H, self.W, pl.ld, st)
     elif kind == 'pack':
       rc = lib.ct_pack_stem_input(img_ptr, pre_ptr, hm_ptr, C.c_void_p(pl.ptr), self.B, self.H, self.W, st)
+    elif kind == 'pack32':
+      rc = lib.ct_pack_stem_input_f32(img_ptr, pre_ptr, hm_ptr, C.c_void_p(pl.ptr), self.B, self.H, self.W, st)
     elif kind == 'pool':
       x, o = pl
       rc = lib.ct_maxpool2(C.c_void_p(x.ptr), C.c_void_p(o.ptr), self.ct_dtype, self.B, x.H, x.W, x.C,

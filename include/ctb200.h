@@ -66,8 +66,11 @@ typedef enum {           /* per-launch transform applied to the fp32 NCHW head o
 typedef enum {
   CT_ENGINE_SIMT = 0,          /* fp32 FFMA implicit GEMM (reference accuracy; fp32 or bf16 activations) */
   CT_ENGINE_TCGEN05 = 1,       /* tcgen05 implicit GEMM, A gathered per tap (any stride, DCN) */
-  CT_ENGINE_TCGEN05_HALO = 2   /* tcgen05, TMA-loaded halo tile, taps by descriptor shift: stride-1 'same'
+  CT_ENGINE_TCGEN05_HALO = 2,  /* tcgen05, TMA-loaded halo tile, taps by descriptor shift: stride-1 'same'
                                   convs with C_in in {8,16,32,48,64,128,192,256} whose weights fit in smem */
+  CT_ENGINE_TCGEN05_X3 = 3     /* the gather engine on fp32 activations (dtype CT_F32) with bf16 hi/lo split operands:
+                                  D += A_hi B_hi + A_hi B_lo + A_lo B_hi, fp32 accumulate -- ~1e-5 per layer, the
+                                  tensor-core path that meets the reference's fp32 results to 1e-3 end to end */
 } ct_engine;
 
 /* One convolution-like layer.  Activations are NHWC with an explicit pixel stride (ld, in
@@ -110,6 +113,7 @@ int64_t ct_packed_weight_bytes(int32_t engine, int32_t C_out, int32_t C_in, int3
  * SIMT engine : fp32 [KH*KW*C_in (k = tap*C_in + c)][C_out padded to 64].
  * tcgen05     : bf16 tiles [n_tiles][k_slices][n_tile rows x 64 k] in the 128B-swizzled
  *               shared-memory image the MMA descriptor expects (one bulk copy per tile).
+ * tcgen05 x3  : the same with two tiles per K slice: [hi = bf16(w)][lo = bf16(w - hi)].
  * tcgen05 halo: bf16 [n_tiles][K=16 blocks][2 K-cores][n_tile/8][8 rows][8] (un-swizzled K-major core
  *               matrices); block = (tap, 16 channels), or (ky, tap pair) when C_in == 8. */
 int ct_pack_weights(int32_t engine, const float* w_oihw, int32_t C_out, int32_t C_in, int32_t KH,
@@ -129,6 +133,10 @@ int ct_stem_forward(const float* img, const float* pre_img, const float* pre_hm,
  * tensor-core stem (CT_ENGINE_TCGEN05_HALO, 7x7, C_in = 8, epilogue_sum3).  NULL inputs give zeros. */
 int ct_pack_stem_input(const float* img, const float* pre_img, const float* pre_hm, void* out, int32_t B,
                        int32_t H, int32_t W, void* stream);
+
+/* the same packing in fp32 (NHWC [B,H,W,8] floats): stem input of CT_ENGINE_TCGEN05_X3 */
+int ct_pack_stem_input_f32(const float* img, const float* pre_img, const float* pre_hm, float* out, int32_t B,
+                           int32_t H, int32_t W, void* stream);
 
 int ct_maxpool2(const void* x, void* out, int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t C,
                 int32_t ld_in, int32_t ld_out, void* stream);

@@ -20,8 +20,9 @@ def run_conv(engine, dtype, x_nchw, w, bias, stride, relu=True, residual=None, a
   xb[..., ch_off:ch_off + Cin] = x_nchw.permute(0, 2, 3, 1).to(act)
   pad = k // 2
   OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
-  if engine in (L.CT_ENGINE_TCGEN05, L.CT_ENGINE_TCGEN05_HALO) and n_tile == 0:
-    n_tile = min(256 if engine == L.CT_ENGINE_TCGEN05 else 128, (O + 15) // 16 * 16)
+  if engine in (L.CT_ENGINE_TCGEN05, L.CT_ENGINE_TCGEN05_HALO, L.CT_ENGINE_TCGEN05_X3) and n_tile == 0:
+    cap = 256 if engine == L.CT_ENGINE_TCGEN05 or (engine == L.CT_ENGINE_TCGEN05_X3 and a_mode != L.CT_A_DCN) else 128
+    n_tile = min(cap, (O + 15) // 16 * 16)
   nbytes = lib.ct_packed_weight_bytes(engine, O, Cin, k, k, n_tile)
   wp = torch.empty(nbytes, dtype=torch.uint8)
   w32 = w.float().contiguous()
