@@ -184,7 +184,7 @@ def _op_flops(kind, pl, L):
 def _op_group(kind, pl, L):
   if kind != 'conv':
     return kind
-  if pl.a_mode == L.CT_A_DCN:
+  if pl.a_mode in (L.CT_A_DCN, L.CT_A_DCN_WIN):
     return 'dcn_main'
   return {L.CT_ENGINE_TCGEN05: 'conv_tc', L.CT_ENGINE_TCGEN05_HALO: 'conv_halo', L.CT_ENGINE_SIMT: 'conv_simt',
           L.CT_ENGINE_TCGEN05_X3: 'conv_tc'}[pl.engine]

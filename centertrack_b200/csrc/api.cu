@@ -121,8 +121,9 @@ extern "C" int ct_conv_forward(const ct_conv_desc* d, void* stream) {
   }
   CT_REQUIRE(d->ld_in >= d->C_in, "ld_in < C_in");
   CT_REQUIRE(d->out_mode == CT_OUT_NCHW_F32 || d->ld_out >= (d->epilogue_sum3 ? 16 : d->C_out), "ld_out < C_out");
-  if (d->a_mode == CT_A_DCN) {
+  if (d->a_mode == CT_A_DCN || d->a_mode == CT_A_DCN_WIN) {
     CT_REQUIRE(d->om != nullptr && d->ld_om >= 27, "DCN needs om with ld_om >= 27");
+    CT_REQUIRE(d->a_mode == CT_A_DCN || d->engine == CT_ENGINE_TCGEN05, "CT_A_DCN_WIN: bf16 tcgen05 engine only");
     CT_REQUIRE(d->KH == 3 && d->KW == 3 && d->stride == 1 && d->pad == 1, "DCN is 3x3 s1 p1");
   }
   cudaStream_t st = (cudaStream_t)stream;

@@ -64,6 +64,11 @@ __device__ __forceinline__ float head_transform(float v, int head_act, float dep
   return v;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda at link time)
+typedef int (*TmapEncodeFnRaw)(void*, int, unsigned, void*, const unsigned long long*, const unsigned long long*,
+                               const unsigned*, const unsigned*, int, int, int, int);
+void* tmap_encode_raw();
+
 int conv_forward_simt(const ct_conv_desc* d, cudaStream_t st);
 int conv_forward_tc(const ct_conv_desc* d, cudaStream_t st);
 int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st);

@@ -508,15 +508,17 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
+void* tmap_encode_raw();
+static EncodeTiledFn get_encode() { return reinterpret_cast<EncodeTiledFn>(tmap_encode_raw()); }
+void* tmap_encode_raw() {
+  static void* fn = nullptr;
   if (fn) return fn;
   void* p = nullptr;
   cudaDriverEntryPointQueryResult q;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
       q != cudaDriverEntryPointSuccess)
     return nullptr;
-  fn = reinterpret_cast<EncodeTiledFn>(p);
+  fn = p;
   return fn;
 }
 

@@ -71,6 +71,7 @@ class DLA34Engine(object):
     self.ct_dtype = L.CT_BF16 if precision == 'bf16' else L.CT_F32
     self.engine = {'bf16': L.CT_ENGINE_TCGEN05, 'fp32': L.CT_ENGINE_SIMT, 'bf16x3': L.CT_ENGINE_TCGEN05_X3}[precision]
     self.x3 = (precision == "bf16x3")
+    self.dcn_window = bool(int(__import__('os').environ.get('CTB_DCN_WINDOW', '1')))
     self.depth_scale = float(depth_scale)
     self.has_pre_img = has_pre_img and ('base.pre_img_layer.0.weight' in self.sd)
     self.has_pre_hm = has_pre_hm and ('base.pre_hm_layer.0.weight' in self.sd)
@@ -131,7 +132,8 @@ class DLA34Engine(object):
     return self._dev(dst)
 
   def _conv(self, name, x, w, shift, out, k, stride=1, relu=True, residual=None, a_mode=L.CT_A_CONV,
-            om=None, out_mode=L.CT_OUT_NHWC, head_act=L.CT_HEAD_NONE, sig_from=1 << 30, c_out=None, sum3=0):
+            om=None, out_mode=L.CT_OUT_NHWC, head_act=L.CT_HEAD_NONE, sig_from=1 << 30, c_out=None, sum3=0,
+            w_pack=None):
     """Append one conv-like launch.  x: TV; out: TV (NHWC modes) or fp32 tensor (NCHW)."""
     C_in = x.C
     if w.shape[1] != C_in:      # input channels padded (never happens for DLA-34 tensors)
@@ -168,7 +170,7 @@ class DLA34Engine(object):
     d.depth_scale = self.depth_scale
     d.n_tile = n_tile
     d.x = x.ptr
-    d.w = self._pack(w, n_tile, engine).data_ptr()
+    d.w = self._pack(w if w_pack is None else w_pack, n_tile, engine).data_ptr()
     sh = self._dev(shift.to(torch.float32).contiguous())
     d.shift = sh.data_ptr()
     if residual is not None:
@@ -210,7 +212,15 @@ class DLA34Engine(object):
                sd[p + '.conv.conv_offset_mask.bias'], om, 3, 1, relu=False,
                out_mode=L.CT_OUT_NHWC_F32, sig_from=18)
     w, shift = self._fold(p + '.conv', p + '.actf.0')
-    self._conv(p, x, w, shift, out, 3, 1, relu=True, a_mode=L.CT_A_DCN, om=om)
+    # window sampler unless its smem footprint (18 KB table + 43 KB window + stages) would halve the occupancy of a
+    # layer whose N tile is wide and whose input needs two window refills (128 -> 128 at 64x64: measured 155 vs 136 us)
+    if self.engine == L.CT_ENGINE_TCGEN05 and x.C % 64 == 0 and self.dcn_window and not (x.C == 128 and w.shape[0] == 128):
+      # sample from a TMA-staged shared-memory window; K order = (64-channel chunk, tap, channel)
+      nch = x.C // 64
+      w_cm = w.reshape(w.shape[0], nch, 64, 3, 3).permute(0, 2, 1, 3, 4).reshape(w.shape[0], 64, nch * 3, 3)
+      self._conv(p, x, w, shift, out, 3, 1, relu=True, a_mode=L.CT_A_DCN_WIN, om=om, w_pack=w_cm.contiguous())
+    else:
+      self._conv(p, x, w, shift, out, 3, 1, relu=True, a_mode=L.CT_A_DCN, om=om)
 
   def _node(self, p, x, out, which):
     """IDAUp's proj (which=0) / node (which=1) module by --dla_node (dla.py:588-592): DeformConv | Conv | GlobalConv."""

@@ -47,7 +47,12 @@ typedef enum { CT_F32 = 0, CT_BF16 = 1 } ct_dtype;
 /* How the A operand (rows = output pixels, K = taps x C_in) of the implicit GEMM is formed. */
 typedef enum {
   CT_A_CONV = 0,  /* plain KxK window, stride/pad */
-  CT_A_DCN = 1    /* 3x3 s1 p1 modulated-deformable bilinear sampling driven by `om` */
+  CT_A_DCN = 1,   /* 3x3 s1 p1 modulated-deformable bilinear sampling driven by `om` */
+  CT_A_DCN_WIN = 2 /* the same operator on the bf16 tcgen05 engine with the input neighbourhood of each 8x16-pixel
+                      output patch staged in shared memory by TMA (samples displaced by more than the margin fall
+                      back to global memory).  Needs C_in % 64 == 0 and weights packed 64-channel-chunk-major:
+                      ct_pack_weights(engine, w', C_out, 64, 3 * C_in / 64, 3, ...) with
+                      w'[o][c][chunk * 3 + ky][kx] = w[o][chunk * 64 + c][ky][kx] */
 } ct_a_mode;
 
 /* Epilogue / output format. */

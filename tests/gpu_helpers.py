@@ -23,10 +23,15 @@ def run_conv(engine, dtype, x_nchw, w, bias, stride, relu=True, residual=None, a
   if engine in (L.CT_ENGINE_TCGEN05, L.CT_ENGINE_TCGEN05_HALO, L.CT_ENGINE_TCGEN05_X3) and n_tile == 0:
     cap = 256 if engine == L.CT_ENGINE_TCGEN05 or (engine == L.CT_ENGINE_TCGEN05_X3 and a_mode != L.CT_A_DCN) else 128
     n_tile = min(cap, (O + 15) // 16 * 16)
-  nbytes = lib.ct_packed_weight_bytes(engine, O, Cin, k, k, n_tile)
-  wp = torch.empty(nbytes, dtype=torch.uint8)
   w32 = w.float().contiguous()
-  L.check(lib.ct_pack_weights(engine, C.c_void_p(w32.data_ptr()), O, Cin, k, k, n_tile, C.c_void_p(wp.data_ptr())))
+  pc, pkh, pkw = Cin, k, k
+  if a_mode == L.CT_A_DCN_WIN:        # 64-channel-chunk-major K order (include/ctb200.h)
+    nch = Cin // 64
+    w32 = w32.reshape(O, nch, 64, 3, 3).permute(0, 2, 1, 3, 4).reshape(O, 64, nch * 3, 3).contiguous()
+    pc, pkh, pkw = 64, nch * 3, 3
+  nbytes = lib.ct_packed_weight_bytes(engine, O, pc, pkh, pkw, n_tile)
+  wp = torch.empty(nbytes, dtype=torch.uint8)
+  L.check(lib.ct_pack_weights(engine, C.c_void_p(w32.data_ptr()), O, pc, pkh, pkw, n_tile, C.c_void_p(wp.data_ptr())))
   wp = wp.to(dev)
   sh = bias.float().contiguous().to(dev)
   d = L.ConvDesc()

@@ -71,14 +71,19 @@ def test_head_1x1_writes_reference_layout_with_fused_activation(eng, cout_act):
   _close(got, ref, tol * (10 if act == 2 else 1))
 
 
-@pytest.mark.parametrize('eng', [ENGINES[0], ENGINES[2], ENGINES[3]], ids=['simt_f32', 'tcgen05', 'tcgen05_x3'])
+DCN_ENGINES = [ENGINES[0], ENGINES[2], ENGINES[2] + ('win',), ENGINES[3]]
+
+
+@pytest.mark.parametrize('eng', DCN_ENGINES, ids=['simt_f32', 'tcgen05', 'tcgen05_window', 'tcgen05_x3'])
 @pytest.mark.parametrize('shape', [(1, 64, 64, 24, 40), (2, 128, 64, 16, 16), (1, 256, 256, 8, 12),
-                                   (1, 512, 256, 4, 6), (1, 64, 64, 5, 7), (2, 64, 64, 24, 32)])
+                                   (1, 512, 256, 4, 6), (1, 64, 64, 5, 7), (2, 64, 64, 24, 32), (3, 64, 128, 40, 56)])
 def test_dcn_v2(eng, shape):
   """Offset/mask conv + modulated deformable conv; large offsets push samples across and beyond the
-  border (zero padding, partial bilinear weights)."""
+  border (zero padding, partial bilinear weights) and, for the shared-memory-window variant (CT_A_DCN_WIN), beyond
+  the staged window (global fall-back path) -- ragged 8x16 patches included."""
   from gpu_helpers import run_conv
-  _, engine, dtype, tol = eng
+  _, engine, dtype, tol = eng[:4]
+  dcn_mode = L.CT_A_DCN_WIN if len(eng) > 4 else L.CT_A_DCN
   B, Cin, Cout, H, W = shape
   g = torch.Generator().manual_seed(H * W)
   x = torch.randn(B, Cin, H, W, generator=g)
@@ -97,12 +102,12 @@ def test_dcn_v2(eng, shape):
   om_dev = om.permute(0, 2, 3, 1).contiguous()
   omc = om.cpu()
   assert float(omc[:, :18].abs().max()) > 2.0          # the case really leaves the 3x3 window
-  cols = co.dcn_sample_columns(xq, omc[:, :18], omc[:, 18:27])
+  cols = co.dcn_sample_columns(xq, omc[:, :18], omc[:, 18:27], bf16_blend=tc)      # both bf16 samplers blend in packed bf16
   if tc:
     cols = cols.bfloat16().float()
   ref = torch.einsum('ok,bkp->bop', wq.reshape(Cout, Cin * 9), cols.reshape(B, Cin * 9, H * W)).view(B, Cout, H, W)
   ref = F.relu(ref + b.view(1, -1, 1, 1))
-  got = run_conv(engine, dtype, x.cuda(), w, b, 1, relu=True, a_mode=L.CT_A_DCN, om=om_dev)
+  got = run_conv(engine, dtype, x.cuda(), w, b, 1, relu=True, a_mode=dcn_mode, om=om_dev)
   _close(got, ref, (1e-4 if engine == L.CT_ENGINE_TCGEN05_X3 else 5e-5) if not tc else 8e-3)
 
 

@@ -1,35 +1,48 @@
-"""One eager step (no CUDA graph) of the bf16 hot path for ncu captures:
-   ncu --set full --clock-control none --import-source on -k regex:conv_ -s N -c M -o gpurun_out/prof python tools/profile_step.py"""
+"""One eager step of the benchmarked plan (B frames x HxW, bf16, device tracking) between cudaProfilerStart/Stop, for
+    ncu --profile-from-start off --set full --clock-control none --import-source on -o gpurun_out/r02_step \
+        python tools/profile_step.py [--config coco_tracking] [--batch 32] [--precision bf16]
+It prints the op list in launch order (index, kind, name, engine, a_mode) so that tools/ncu_summary.py can label the
+launches of the capture."""
+import argparse
 import os
 import sys
 
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, 'tests'))
+for p in (ROOT, os.path.join(ROOT, 'tests')):
+  sys.path.insert(0, p)
 
-from centertrack_b200 import synthetic as syn          # noqa
-from centertrack_b200.decode import generic_decode     # noqa
-from helpers import make_model                         # noqa
+from bench import CONFIGS, K                                   # noqa: E402
+from centertrack_b200 import synthetic as wt                    # noqa: E402
+from centertrack_b200.runner import StreamRunner                # noqa: E402
+from helpers import make_model                                  # noqa: E402
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+ap = argparse.ArgumentParser()
+ap.add_argument('--config', default='coco_tracking')
+ap.add_argument('--batch', type=int, default=32)
+ap.add_argument('--precision', default='bf16')
+args = ap.parse_args()
+H, W = CONFIGS[args.config][:2]
 dev = torch.device('cuda')
-opt, model, sd = make_model('coco_tracking')
+opt, model, sd = make_model(args.config)
 model = model.to(dev)
-eng = model.engine_for(B, 512, 512, dev, 'bf16')
-eng.set_fused_activations(True)
-img, pre, hm = syn.synthetic_inputs(1, 512, 512)
-g = torch.Generator().manual_seed(0)
-x = (img + 0.05 * torch.randn(B, 3, 512, 512, generator=g)).to(dev)
-p = (pre + 0.05 * torch.randn(B, 3, 512, 512, generator=g)).to(dev)
-h = hm.expand(B, 1, 512, 512).contiguous().to(dev)
-for _ in range(steps):
-  out = dict(eng.forward(x, p, h))
-  generic_decode(out, K=100)
+runner = StreamRunner(model, args.batch, H, W, K=K, precision=args.precision, device=dev, opt=opt, device_tracking=True,
+                      use_graph=False)
+img, pre, hm = wt.synthetic_inputs(2, H, W, seed=317)
+for s in range(3):
+  runner.load_device_inputs(img[s & 1:(s & 1) + 1].expand(args.batch, 3, H, W).contiguous().to(dev), None, s)
+for _ in range(3):                 # warm: first-frame path, then two steady-state steps (tracks exist)
+  runner.step_device()
 torch.cuda.synchronize()
-names = [(k, n) for k, pl, n in eng.ops]
-print('ops per step:', len(names))
-for i, (k, n) in enumerate(names):
-  print(i, k, n)
+print('OPS')
+print(0, 'memset+render', 'ct_render_tracks')
+for i, (kind, pl, name) in enumerate(runner.eng.ops):
+  print(i + 1, kind, name, getattr(pl, 'engine', ''), getattr(pl, 'a_mode', ''))
+print(len(runner.eng.ops) + 1, 'decode', 'ct_decode')
+print(len(runner.eng.ops) + 2, 'track', 'ct_track_step')
+sys.stdout.flush()
+torch.cuda.cudart().cudaProfilerStart()
+runner.step_device()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
