@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include "../../include/ctb200.h"
 
 namespace ctb {
@@ -39,6 +40,33 @@ inline int after_launch() {
     return fail(CT_ERR_CUDA, "kernel launch failed: %s (%ld)", cudaGetErrorString(e), (long)e);
   }
   return CT_OK;
+}
+
+// ---- programmatic dependent launch (PDL): a kernel launched with the attribute may start while its predecessor in
+// the stream is still running; it must execute pdl_wait() before touching anything the predecessor produces (or
+// writing anything the predecessor may still read).  What runs before the wait -- shared-memory carve-up, mbarrier
+// init, TMEM allocation, the halo engine's weight load -- overlaps the predecessor's tail.  pdl_trigger() lets the
+// NEXT kernel of the stream do the same with us.  CTB_PDL=0 launches everything stream-serialised (no overlap).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static const int on = getenv("CTB_PDL") ? atoi(getenv("CTB_PDL")) : 1;
+  return on != 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                 Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 // ---- element type helpers -----------------------------------------------------------

@@ -212,6 +212,7 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + off_bar + 8 * (9 + 2 * S));
   const int NACC = a.nacc;
 
+  pdl_trigger();                       // the next kernel of the stream may start its own prologue now
   if (tid == 0) {
     h_mbar_init(w_full, 1);
     for (int s = 0; s < S; ++s) { h_mbar_init(halo_full(s), 1); h_mbar_init(halo_empty(s), 1); }
@@ -234,6 +235,13 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
   __syncthreads();
   h_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // the weights are constants: their bulk copy goes out BEFORE waiting for the previous kernel (PDL), so that it
+  // overlaps that kernel's tail; everything after the wait reads activations the previous kernel produced
+  if (warp == 8 && lane == 0) {
+    h_mbar_expect_tx(w_full, a.w_bytes);
+    h_bulk_g2s(sW, reinterpret_cast<const unsigned char*>(a.w) + (size_t)(blockIdx.x % a.n_tiles_n) * a.w_bytes, a.w_bytes, w_full);
+  }
+  pdl_wait();
 
   // work items: n-tile major so that a CTA keeps ONE weight tile resident:  item = nt * spatial + sp
   // CTA c handles n-tile (c % n_tiles_n) and spatial tiles (c / n_tiles_n) + i * (gridDim.x / n_tiles_n)
@@ -247,8 +255,6 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
   if (warp == 8) {
     if (lane == 0) {
       // ===================== TMA producer =====================
-      h_mbar_expect_tx(w_full, a.w_bytes);
-      h_bulk_g2s(sW, reinterpret_cast<const unsigned char*>(a.w) + (size_t)nt * a.w_bytes, a.w_bytes, w_full);
       int it = 0;
       for (int sp = sp0; sp < sp_total; sp += sp_stride, ++it) {
         const int s = it % S;
@@ -700,7 +706,7 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
   if (groups < 1) groups = 1;
   if (groups > a.tiles_total) groups = a.tiles_total;
   const int grid = (int)(groups * a.n_tiles_n);
-  conv_halo_kernel<<<grid, H_THREADS, smem, st>>>(a, tmap);
+  CT_CUDA_OK(launch_kernel(conv_halo_kernel, dim3(grid), dim3(H_THREADS), smem, st, true, a, tmap));
   return after_launch();
 }
 

@@ -283,6 +283,7 @@ conv_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
   const int nt = blockIdx.y;
   const int n0 = nt * a.n_tile;
   if (tid == 0) tc_stamp(0);
+  pdl_trigger();                       // the next kernel of the stream may start its own prologue now
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), TC_PRODUCERS / 32); mbar_init(empty_bar(s), 1); }
@@ -302,6 +303,7 @@ conv_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (tid == 0) tc_stamp(7);
+  pdl_wait();                          // everything below reads what the previous kernel wrote
 
   if (warp < 8) {
     // =========================== A producers ===========================
@@ -1025,8 +1027,8 @@ int conv_forward_tc(const ct_conv_desc* d, cudaStream_t st) {
     if (cr != CUDA_SUCCESS) return fail(CT_ERR_CUDA, "conv_tc: cuTensorMapEncodeTiled failed%s (%ld)", "", (long)cr);
   }
   dim3 grid(m_tiles, n_tiles);
-  if (x3) conv_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(a, tmap);
-  else conv_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(a, tmap);
+  if (x3) CT_CUDA_OK(launch_kernel(conv_tc_kernel<true>, grid, dim3(TC_THREADS), smem, st, true, a, tmap));
+  else CT_CUDA_OK(launch_kernel(conv_tc_kernel<false>, grid, dim3(TC_THREADS), smem, st, true, a, tmap));
   return after_launch();
 }
 

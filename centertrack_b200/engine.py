@@ -72,6 +72,7 @@ class DLA34Engine(object):
     self.engine = {'bf16': L.CT_ENGINE_TCGEN05, 'fp32': L.CT_ENGINE_SIMT, 'bf16x3': L.CT_ENGINE_TCGEN05_X3}[precision]
     self.x3 = (precision == "bf16x3")
     self.dcn_window = bool(int(__import__('os').environ.get('CTB_DCN_WINDOW', '1')))
+    self.ntile_cap = int(__import__('os').environ.get('CTB_NTILE_CAP', '256'))
     self.depth_scale = float(depth_scale)
     self.has_pre_img = has_pre_img and ('base.pre_img_layer.0.weight' in self.sd)
     self.has_pre_hm = has_pre_hm and ('base.pre_hm_layer.0.weight' in self.sd)
@@ -146,6 +147,10 @@ class DLA34Engine(object):
     P = self.B * OH * OW
     engine = self.engine
     n_tile = self._pick_n_tile(P, C_out) if engine in (L.CT_ENGINE_TCGEN05, L.CT_ENGINE_TCGEN05_X3) else 0
+    if engine == L.CT_ENGINE_TCGEN05 and a_mode == L.CT_A_CONV and n_tile > self.ntile_cap:
+      # experiment knob (CTB_NTILE_CAP): 128-wide tiles with two co-resident CTAs measured SLOWER than one 256-wide
+      # CTA on levels 4-5 (conv_tc plain 1.81 vs 1.73 ms per 32-frame step), so the default cap is 256 = no cap
+      n_tile = self.ntile_cap
     if engine == L.CT_ENGINE_TCGEN05_X3 and n_tile > 128 and a_mode == L.CT_A_DCN:
       n_tile = 128            # x3 DCN: two 36 KB-table stages of (32 + 2 x n_tile/8) KB must fit
     if engine == L.CT_ENGINE_TCGEN05 and self.use_halo and a_mode == L.CT_A_CONV and stride == 1 and kh == kw and \

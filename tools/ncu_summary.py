@@ -12,12 +12,15 @@ frames = int(sys.argv[3]) if len(sys.argv) > 3 else 32
 rows = list(csv.reader(open(raw)))
 hdr = rows[0]
 col = {n: i for i, n in enumerate(hdr)}
-data = [r for r in rows[2:] if len(r) == len(hdr)]           # row 1 = units
+units = rows[1]                                               # row 1 = one (scaled) unit per column
+data = [r for r in rows[2:] if len(r) == len(hdr)]
+SCALE = {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 's': 1e6,          # times -> us
+         'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}   # sizes -> bytes
 
 
 def num(r, name):
   try:
-    return float(r[col[name]].replace(',', ''))
+    return float(r[col[name]].replace(',', '')) * SCALE.get(units[col[name]], 1.0)
   except Exception:
     return float('nan')
 
@@ -36,12 +39,14 @@ j = 0
 for r in kern:
   name = r[col['Kernel Name']].split('(')[0]
   out.append({'kernel': name, 'grid': r[col['Grid Size']] if 'Grid Size' in col else '',
-              'us': num(r, 'gpu__time_duration.sum') / 1000.0,
+              'us': num(r, 'gpu__time_duration.sum'),
               'dram_rd': num(r, 'dram__bytes_read.sum'), 'dram_wr': num(r, 'dram__bytes_write.sum'),
               'tensor_pct': num(r, 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed') if
               'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed' in col else float('nan'),
               'issue_pct': num(r, 'sm__inst_issued.avg.pct_of_peak_sustained_active') if
-              'sm__inst_issued.avg.pct_of_peak_sustained_active' in col else float('nan')})
+              'sm__inst_issued.avg.pct_of_peak_sustained_active' in col else float('nan'),
+              'lsu_pct': num(r, 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed') if
+              'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed' in col else float('nan')})
 # label: the conv launches appear in plan order; non-conv kernels by name
 conv_ops = [o for o in ops if o[0] == 'conv']
 ci = 0
@@ -68,10 +73,10 @@ print('| group | launches | us | share | DRAM read MB | DRAM written MB | tensor
 for k, g in sorted(groups.items(), key=lambda kv: -kv[1]['us']):
   print('| %s | %d | %.1f | %.1f %% | %.1f | %.1f | %.1f |' % (k, g['n'], g['us'], 100 * g['us'] / tot, g['rd'] / 1e6, g['wr'] / 1e6,
                                                              g['tw'] / max(g['us'], 1e-9)))
-print('\n| # | op | kernel | grid | us | DRAM rd MB | DRAM wr MB | tensor % | issue % |\n|---|---|---|---|---|---|---|---|---|')
+print('\n| # | op | kernel | grid | us | DRAM rd MB | DRAM wr MB | tensor % | issue % | L1/smem data pipe % |\n|---|---|---|---|---|---|---|---|---|---|')
 for i, o in enumerate(out):
-  print('| %d | %s | %s | %s | %.1f | %.1f | %.1f | %.1f | %.1f |' % (i, o['op'], o['kernel'][-28:], o['grid'], o['us'], o['dram_rd'] / 1e6,
-                                                                     o['dram_wr'] / 1e6, o['tensor_pct'], o['issue_pct']))
+  print('| %d | %s | %s | %s | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f |' % (i, o['op'], o['kernel'][-28:], o['grid'], o['us'], o['dram_rd'] / 1e6,
+                                                                            o['dram_wr'] / 1e6, o['tensor_pct'], o['issue_pct'], o['lsu_pct']))
 tj = os.path.join(os.path.dirname(os.path.abspath(raw)), 'traffic.json')
 cur = json.load(open(tj)) if os.path.exists(tj) else {}
 cfg = os.environ.get('CT_CFG', 'coco_tracking')
