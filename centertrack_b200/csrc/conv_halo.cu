@@ -225,7 +225,7 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // folded-BN shift / bias of this CTA's output-channel tile, staged once (read as float4 broadcasts)
-  float* s_shift = reinterpret_cast<float*>(sm + off_bar + 256);      // barriers + TMEM slot use < 256 bytes (S <= 4)
+  float* s_shift = reinterpret_cast<float*>(sm + off_bar + 256);      // barriers + TMEM slot use 204 bytes at S = 8 (< 256)
   {
     const int n0s = (blockIdx.x % a.n_tiles_n) * a.n_tile;
     for (int j = tid; j < 256; j += H_THREADS)
@@ -641,7 +641,11 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
   int stages;
   if (a.mma_warps == 2 && a.nblk <= 16) a.mma_warps = 1;
   if (a.mma_warps == 2) {
-    stages = (smem_for(4) <= 220 * 1024 && ctas_for(4) == ctas_for(2)) ? 4 : 2;
+    // as many (even) stages as keep the CTAs-per-SM count: the TMA of a thin-channel halo (32-byte rows) takes ~4200
+    // cycles to land (tools/halo_trace.py, level0), so with two stages per MMA warp the item period WAS the TMA latency / 2
+    stages = 2;
+    for (int sdeep = 8; sdeep >= 4; sdeep -= 2)
+      if (smem_for(sdeep) <= 220 * 1024 && ctas_for(sdeep) == ctas_for(2)) { stages = sdeep; break; }
   } else {
     stages = 3;
     while (stages > 2 && smem_for(stages) > 220 * 1024) --stages;
