@@ -7,14 +7,15 @@
 //   key = (float_bits(value) << 32) | (0xFFFFFFFF - index)        (values are >= 0 after sigmoid)
 // so indices are bit-exact with the oracle on every input, ties included.
 //
-// grid = (C + J planes, B); each CTA streams one class plane through shared memory once (the only
-// HBM read of hm), selects its top-K; the last CTA of a batch element to finish merges the C*K
-// candidates and writes the K records.
+// grid = (C + J planes, B); each CTA streams one class plane from HBM once, straight into registers (rolling
+// 3-row NMS, 16-byte loads, neighbours by shuffle), compacts the kept positive peaks as 64-bit keys into shared
+// memory and selects its top-K there; the last CTA of a batch element to finish merges the C*K candidates by
+// (value, class, index) and writes the K records.
 #include "common.cuh"
 
 namespace ctb {
 
-constexpr int DT = 512;          // threads per CTA
+constexpr int DT = 512;          // threads per CTA (3 CTAs per SM: 40 registers, 37 KB of shared memory each)
 constexpr int MAXK = 512;
 constexpr int PEAK_CAP = 4096;   // compact list of kept positive peaks (indices), 16 KB
 
@@ -130,7 +131,7 @@ __device__ __forceinline__ bool nms_keep(const float* sp, int i, int H, int W) {
   return m == c;
 }
 
-__global__ void __launch_bounds__(DT)
+__global__ void __launch_bounds__(DT, 3)
 decode_kernel(DecodeArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int hist[256];
@@ -146,92 +147,116 @@ decode_kernel(DecodeArgs a) {
   const int H = d.H, W = d.W, HW = H * W, K = d.K, NP = d.C + d.J;
 
   // ------------------------------ phase 1: one plane ------------------------------
+  // The plane is STREAMED from HBM exactly once, straight into registers (no shared-memory staging): each warp owns a
+  // band of rows; a lane holds 4 consecutive pixels of a row (16-byte load), gets its row neighbours by shuffle, and
+  // rolls the 3-wide row maxima of the rows above / at / below through registers -- the 3x3 max-equals NMS costs
+  // ~0.45 instructions per pixel.  Kept positive peaks (~1 pixel in 10) are compacted as ready-made 64-bit keys
+  // (value bits, ~index) into a shared list; the exact radix select runs over that list.
   {
-    float* sp = reinterpret_cast<float*>(smem_raw);
     const float* src = pl < d.C ? d.hm + ((size_t)b * d.C + pl) * HW
                                 : d.hm_hp + ((size_t)b * d.J + (pl - d.C)) * HW;
-    if ((HW & 3) == 0 && (reinterpret_cast<size_t>(src) & 15) == 0) {
-      const float4* s4 = reinterpret_cast<const float4*>(src);
-      float4* d4 = reinterpret_cast<float4*>(sp);
-      for (int i = tid; i < (HW >> 2); i += DT) d4[i] = __ldg(s4 + i);
-    } else {
-      for (int i = tid; i < HW; i += DT) sp[i] = __ldg(src + i);
-    }
-    if (tid == 0) peak_n = 0;
+    unsigned long long* klist = reinterpret_cast<unsigned long long*>(smem_raw);
+    if (tid == 0) { peak_n = 0; sel_n = 0; }
+    for (int i = tid; i < a.kpad; i += DT) sel[i] = 0ull;
     __syncthreads();
-    // heat * keep as a sort key: -0.0 cannot occur for sigmoid outputs; clamp negatives (not produced by the
-    // reference path) to 0 so the unsigned key order stays valid.  Only the degenerate general path evaluates
-    // the 3x3 NMS through this function; the fast path below does it with rolling row maxima.
-    auto keyfn = [&](int i) -> unsigned long long {
-      const float v = nms_keep(sp, i, H, W) ? sp[i] : 0.f;
-      const unsigned vb = v > 0.f ? __float_as_uint(v) : 0u;
-      return ((unsigned long long)vb << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
-    };
-    // Fast path: after NMS only the kept, positive peaks (~1 element in 10) can enter the top-K.  Compact their
-    // indices once and select over that short list; it is exact whenever there are >= K such peaks (zeros, which
-    // the index-ordered tie rule would otherwise have to rank, are then out of the race).  Degenerate planes
-    // (fewer than K positive peaks, or more than the list holds) take the general path over all H*W keys.
-    // NMS + compaction in ONE pass: thread = one column of a band of rows; the 3-wide row maxima of the rows above /
-    // at / below roll through registers (3 conflict-free shared loads + 4 max per element, no division).
-    unsigned* plist = reinterpret_cast<unsigned*>(smem_raw + (size_t)HW * 4);
-    bool listed = false;
-    if (W <= DT) {
-      listed = true;
-      const int nb = DT / W;                               // bands of rows
-      const int band = tid / W, x = tid - band * W;
-      const int rpb = (H + nb - 1) / nb;                   // rows per band (same trip count for every thread)
-      const int y0 = band * rpb;
-      const bool col_ok = band < nb;
+    const bool vec_ok = (W & 3) == 0 && (reinterpret_cast<size_t>(src) & 15) == 0;
+    if (vec_ok) {
+      const int lane = tid & 31, warp = tid >> 5;
+      constexpr int NW = DT / 32;
+      const int rpw = (H + NW - 1) / NW;
+      const int y0 = warp * rpw;
       const float NEG = __int_as_float(0xff800000);
-      auto rowmax = [&](int y) -> float {
-        if (!col_ok || y < 0 || y >= H) return NEG;
-        const float* r = sp + y * W;
-        float m = r[x];
-        if (x > 0) m = fmaxf(m, r[x - 1]);
-        if (x + 1 < W) m = fmaxf(m, r[x + 1]);
-        return m;
-      };
-      float up = rowmax(y0 - 1), cur = rowmax(y0);
-      for (int j = 0; j < rpb; ++j) {
-        const int y = y0 + j;
-        const float dn = rowmax(y + 1);
-        const bool in = col_ok && y < H;
-        const float c = in ? sp[y * W + x] : 0.f;
-        const bool pk = in && c > 0.f && fmaxf(fmaxf(up, cur), dn) == c;
-        const unsigned m = __ballot_sync(0xffffffffu, pk);
-        if (m) {
-          int base = 0;
-          if ((tid & 31) == 0) base = atomicAdd(&peak_n, __popc(m));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (pk) {
-            const int slot = base + __popc(m & ((1u << (tid & 31)) - 1u));
-            if (slot < PEAK_CAP) plist[slot] = (unsigned)(y * W + x);
+      for (int x0 = 0; x0 < W; x0 += 128) {
+        const int x = x0 + 4 * lane;
+        const bool xin = x < W;
+        // One row ahead of its use.  Measured (32 x 80 x 128 x 128 per launch): this form at 3 CTAs/SM 133 us; raw rows
+        // fetched three ahead at 2 CTAs/SM (64 registers), or 4 CTAs of 256 threads, 157 us -- occupancy beats depth here
+        auto load_row = [&](int y, float4& v, float4& h) {
+          const bool yin = y >= 0 && y < H;                                    // warp-uniform
+          v = make_float4(NEG, NEG, NEG, NEG);
+          if (yin && xin) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)y * W + x));
+          float l = __shfl_up_sync(0xffffffffu, v.w, 1), r = __shfl_down_sync(0xffffffffu, v.x, 1);
+          if (lane == 0) l = (yin && x0 > 0) ? __ldg(src + (size_t)y * W + x0 - 1) : NEG;
+          if (lane == 31) r = (yin && x + 4 < W) ? __ldg(src + (size_t)y * W + x + 4) : NEG;
+          h.x = fmaxf(fmaxf(l, v.x), v.y); h.y = fmaxf(fmaxf(v.x, v.y), v.z);
+          h.z = fmaxf(fmaxf(v.y, v.z), v.w); h.w = fmaxf(fmaxf(v.z, v.w), r);
+        };
+        float4 v_cur, h_up, h_cur, v_dn, h_dn;
+        load_row(y0 - 1, v_cur, h_up);
+        load_row(y0, v_cur, h_cur);
+        for (int j = 0; j < rpw; ++j) {
+          const int y = y0 + j;
+          load_row(y + 1, v_dn, h_dn);
+          if (y < H) {                                                         // warp-uniform
+            const float vc[4] = {v_cur.x, v_cur.y, v_cur.z, v_cur.w};
+            const float mx[4] = {fmaxf(fmaxf(h_up.x, h_cur.x), h_dn.x), fmaxf(fmaxf(h_up.y, h_cur.y), h_dn.y),
+                                 fmaxf(fmaxf(h_up.z, h_cur.z), h_dn.z), fmaxf(fmaxf(h_up.w, h_cur.w), h_dn.w)};
+            unsigned bits = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) bits |= (xin && vc[c] > 0.f && mx[c] == vc[c]) ? (1u << c) : 0u;
+            const int cnt = __popc(bits);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const int t = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl += t;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total) {
+              int base = 0;
+              if (lane == 0) base = atomicAdd(&peak_n, total);
+              base = __shfl_sync(0xffffffffu, base, 0);
+              int slot = base + incl - cnt;
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                if (bits & (1u << c)) {
+                  if (slot < PEAK_CAP)
+                    klist[slot] = ((unsigned long long)__float_as_uint(vc[c]) << 32) |
+                                  (unsigned long long)(0xFFFFFFFFu - (unsigned)(y * W + x + c));
+                  ++slot;
+                }
+            }
           }
+          h_up = h_cur; h_cur = h_dn; v_cur = v_dn;
         }
-        up = cur; cur = dn;
       }
     }
     __syncthreads();
     const int npk = peak_n;
-    const bool fast = listed && npk >= K && npk <= PEAK_CAP;
-    if (tid == 0) sel_n = 0;
-    for (int i = tid; i < a.kpad; i += DT) sel[i] = 0ull;
+    // The list is exact whenever it holds at least K peaks and did not overflow (zeros, which the index-ordered tie
+    // rule would otherwise have to rank, are then out of the race).  Degenerate planes (fewer than K positive peaks,
+    // plateaus that overflow the list, odd widths) select over all H*W keys, evaluating the NMS from global memory.
+    const bool fast = vec_ok && npk >= K && npk <= PEAK_CAP;
     if (fast) {
-      // listed elements are kept positive peaks: their key needs no NMS test
-      auto keyfn_l = [&](int j) -> unsigned long long {
-        const unsigned i = plist[j];
-        return ((unsigned long long)__float_as_uint(sp[i]) << 32) | (unsigned long long)(0xFFFFFFFFu - i);
-      };
+      auto keyfn_l = [&](int j) -> unsigned long long { return klist[j]; };
       radix_select(npk, K, keyfn_l, hist, &ss);
       const unsigned long long prefix = ss.prefix, mask = ss.mask;
       for (int j = tid; j < npk; j += DT) {
-        const unsigned long long key = keyfn_l(j);
+        const unsigned long long key = klist[j];
         if ((key & mask) >= prefix) {
           const int slot = atomicAdd(&sel_n, 1);
           if (slot < MAXK) sel[slot] = key;
         }
       }
     } else {
+      auto keyfn = [&](int i) -> unsigned long long {
+        const int y = i / W, x = i - y * W;
+        const float c = __ldg(src + i);
+        float m = c;
+        for (int dy = -1; dy <= 1; ++dy) {
+          const int yy = y + dy;
+          if (yy < 0 || yy >= H) continue;
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int xx = x + dx;
+            if (xx >= 0 && xx < W) m = fmaxf(m, __ldg(src + yy * W + xx));
+          }
+        }
+        // heat * keep as a sort key: -0.0 cannot occur for sigmoid outputs; negatives (not produced by the reference
+        // path) are clamped to 0 so the unsigned key order stays valid
+        const float v = (m == c) ? c : 0.f;
+        const unsigned vb = v > 0.f ? __float_as_uint(v) : 0u;
+        return ((unsigned long long)vb << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+      };
       radix_select(HW, K, keyfn, hist, &ss);
       const unsigned long long prefix = ss.prefix, mask = ss.mask;
       for (int i = tid; i < HW; i += DT) {
@@ -243,7 +268,10 @@ decode_kernel(DecodeArgs a) {
       }
     }
     __syncthreads();
-    bitonic_sort_desc(sel, a.kpad);
+    // Class planes leave their K survivors UNSORTED: the cross-class merge orders by (value, class, index), which is
+    // the order of the reference's second top-K over the [C, K] array (ties: class, then rank = index within a class).
+    // Joint planes (pose) are consumed in rank order by the keypoint refinement: those are sorted here.
+    if (pl >= d.C) bitonic_sort_desc(sel, a.kpad);
     unsigned long long* dst = a.cand + ((size_t)b * NP + pl) * K;
     for (int i = tid; i < K; i += DT) dst[i] = sel[i];
   }
@@ -263,7 +291,9 @@ decode_kernel(DecodeArgs a) {
   const int n2 = d.C * K;
   auto key2 = [&](int i) -> unsigned long long {
     const unsigned long long c = __ldcg(candb + i);
-    return (c & 0xFFFFFFFF00000000ull) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+    const unsigned idx = 0xFFFFFFFFu - (unsigned)(c & 0xFFFFFFFFull);
+    const unsigned g = (unsigned)(i / K) * (unsigned)HW + idx;            // class-major global position
+    return (c & 0xFFFFFFFF00000000ull) | (unsigned long long)(0xFFFFFFFFu - g);
   };
   radix_select(n2, K, key2, hist, &ss);
   if (tid == 0) sel_n = 0;
@@ -294,9 +324,9 @@ decode_kernel(DecodeArgs a) {
   for (int k = tid; k < K; k += DT) {
     const unsigned long long key = sel[k];
     const float score = __uint_as_float((unsigned)(key >> 32));
-    const int flat = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
-    const int cls = flat / K;
-    const unsigned idx = 0xFFFFFFFFu - (unsigned)(__ldcg(candb + flat) & 0xFFFFFFFFull);
+    const unsigned gpos = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull);
+    const int cls = (int)(gpos / (unsigned)HW);
+    const unsigned idx = gpos - (unsigned)cls * (unsigned)HW;
     const float xs0 = (float)(idx % (unsigned)W), ys0 = (float)(idx / (unsigned)W);
     float* rec = recb + (size_t)k * F;
     rec[CT_REC_SCORE] = score;
@@ -428,12 +458,13 @@ extern "C" int ct_decode(const ct_decode_desc* d, void* stream) {
   while (kpad < d->K) kpad <<= 1;
   a.kpad = kpad;
   const int HW = d->H * d->W, K = d->K, J = a.d.J;
-  size_t smem1 = (size_t)HW * 4 + (size_t)PEAK_CAP * 4;
+  CT_REQUIRE((long long)d->C * HW < (1ll << 31), "C*H*W must stay below 2^31 (class-major positions in the merge keys)");
+  size_t smem1 = (size_t)PEAK_CAP * 8;
   size_t smem2 = (size_t)(7 * K + 4 * J * K) * 4;
   size_t smem = smem1 > smem2 ? smem1 : smem2;
   if (smem > 200 * 1024)
-    return fail(CT_ERR_UNSUPPORTED, "ct_decode: heat-map plane of %s%ld elements exceeds the shared-memory "
-                                    "staging limit (51000)", "", (long)HW);
+    return fail(CT_ERR_UNSUPPORTED, "ct_decode: K x joints of %s%ld floats exceed the shared-memory scratch of the pose "
+                                    "refinement", "", (long)(4 * J * K));
   cudaStream_t st = (cudaStream_t)stream;
   CT_CUDA_OK(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(d->C + J, d->B);
