@@ -896,6 +896,290 @@ conv_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
   }
 }
 
+// =====================================================================================================================
+// Persistent DCNv2 kernel (CT_A_DCN_WIN layers with a single N tile, bf16 NHWC output): one CTA per SM walks its share
+// of the 8x16-pixel output patches.  What the per-tile kernel above spends outside its slice loop -- TMEM allocation,
+// barrier init, the sampling-table build behind an L2 round trip for `om`, the window TMA, the epilogue: 12 k of 30 k
+// cycles per tile (tools/tc_trace.py) -- is taken off the critical path:
+//   * the window of unit u+2 (unit = tile x 64-channel chunk) is requested when unit u is finished: two windows in
+//     flight, a whole unit (9 slices) of latency cover;
+//   * the sampling table of tile t+1 is built by the producers one tap per slice while they sample tile t
+//     (its `om` values fetched one slice ahead), into the other of two table buffers;
+//   * two TMEM accumulators: four dedicated epilogue warps drain tile t while the producers / MMA work on tile t+1.
+// Warps 0-7 producers (sampling + table + B copies + window TMA), warp 8 MMA issuer, warps 9-12 epilogue.
+// =====================================================================================================================
+constexpr int DP_THREADS = 416;
+constexpr int DP_SA = 3;                 // A/B stages
+
+__device__ __forceinline__ void dp_tile_origin(const TcArgs& a, int tile, int& b, int& ty, int& tx) {
+  const int tpi = a.tiles_x * a.tiles_y;
+  b = tile / tpi;
+  const int t = tile - b * tpi;
+  ty = t / a.tiles_x;
+  tx = t - ty * a.tiles_x;
+}
+
+__global__ void __launch_bounds__(DP_THREADS, 1)
+dcn_persist_kernel(const TcArgs a, const int tiles_total, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const ConvGeom& g = a.g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t b_tile_bytes = (uint32_t)a.n_tile * 128u;
+  const uint32_t win_stride = (a.win_bytes + 127u) & ~127u;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t sA = smem_base;
+  const uint32_t sB = sA + DP_SA * A_STAGE_BYTES;
+  const uint32_t sWin = sB + DP_SA * b_tile_bytes;                       // 1024-aligned (both terms are)
+  const uint32_t off_tab = DP_SA * A_STAGE_BYTES + DP_SA * b_tile_bytes + 2u * win_stride;
+  DcnWinEntry* tabs = reinterpret_cast<DcnWinEntry*>(smem + off_tab);    // [2][9][128]
+  const uint32_t off_bar = off_tab + 2u * 9u * TC_BM * 16u;
+  const uint32_t bars = smem_base + off_bar;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (DP_SA + s); };
+  auto win_full = [&](int i) { return bars + 8u * (2 * DP_SA + i); };
+  auto acc_full = [&](int i) { return bars + 8u * (2 * DP_SA + 2 + i); };
+  auto acc_empty = [&](int i) { return bars + 8u * (2 * DP_SA + 4 + i); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + off_bar + 8 * (2 * DP_SA + 6));
+
+  pdl_trigger();
+  if (tid == 0) {
+    for (int s = 0; s < DP_SA; ++s) { mbar_init(full_bar(s), TC_PRODUCERS / 32); mbar_init(empty_bar(s), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(win_full(i), 1); mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                 "r"((uint32_t)a.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  const int G = gridDim.x;
+  const int nchunks = g.C_in >> 6;
+  const int HWo = g.OH * g.OW;
+  int n_my = 0;                                                          // tiles of this CTA
+  if ((int)blockIdx.x < tiles_total) n_my = (tiles_total - 1 - (int)blockIdx.x) / G + 1;
+  const int n_units = n_my * nchunks;
+
+  if (warp < 8) {
+    // ======================================= producers =======================================
+    const int q = tid & 7, r0 = tid >> 3;
+    const uint32_t swz = (uint32_t)((q ^ (r0 & 7)) << 4);
+    const int trow = tid & (TC_BM - 1), thalf = tid >> 7;                // table: row, tap parity this thread builds
+    const uint32_t pitch = (uint32_t)a.win_pw * 128u;
+    const int gdx = g.ld_in, gdy = g.W * g.ld_in;
+
+    auto issue_window = [&](int u) {                                     // tid 0 only
+      const int t = u / nchunks, ch = u - t * nchunks;
+      int b, ty, tx;
+      dp_tile_origin(a, (int)blockIdx.x + t * G, b, ty, tx);
+      mbar_arrive_expect_tx(win_full(u & 1), a.win_bytes);
+      tma_4d(sWin + (uint32_t)(u & 1) * win_stride, &tmap, ch << 6, tx * 16 - 1 - a.win_m, ty * 8 - 1 - a.win_m, b,
+             win_full(u & 1));
+    };
+    // per-tile constants of the row this thread builds records for
+    struct RowCtx { const float* om; int oy, ox, img, wy0, wx0; bool ok; };
+    auto row_ctx = [&](int tile) -> RowCtx {
+      RowCtx c;
+      int b, ty, tx;
+      dp_tile_origin(a, tile, b, ty, tx);
+      c.oy = ty * 8 + (trow >> 4); c.ox = tx * 16 + (trow & 15);
+      c.ok = tile < tiles_total && c.oy < g.OH && c.ox < g.OW;
+      c.img = b * g.H * g.W;
+      c.wy0 = ty * 8 - 1 - a.win_m; c.wx0 = tx * 16 - 1 - a.win_m;
+      c.om = a.om + (size_t)((b * g.OH + c.oy) * g.OW + c.ox) * g.ld_om;
+      return c;
+    };
+    auto make_entry = [&](const RowCtx& c, int tap, float dy, float dx, float m) -> DcnWinEntry {
+      DcnWinEntry e; e.goff = 0; e.meta = WIN_IN; e.w01 = 0u; e.w23 = 0u;
+      if (c.ok) {
+        const float py = (float)(c.oy - 1 + tap / 3) + dy;
+        const float px = (float)(c.ox - 1 + tap % 3) + dx;
+        if (py > -1.f && py < (float)g.H && px > -1.f && px < (float)g.W) {
+          const float y0f = floorf(py), x0f = floorf(px);
+          const int y0 = (int)y0f, x0 = (int)x0f;
+          const float ly = py - y0f, lx = px - x0f, hy = 1.f - ly, hx = 1.f - lx;
+          const bool y0ok = y0 >= 0, y1ok = y0 + 1 <= g.H - 1, x0ok = x0 >= 0, x1ok = x0 + 1 <= g.W - 1;
+          const int yc = max(y0, 0), xc = max(x0, 0);
+          e.goff = (c.img + yc * g.W + xc) * g.ld_in;
+          const bool ddx = x0ok && x1ok, ddy = y0ok && y1ok;
+          const bool inside = y0 >= c.wy0 && y0 + 1 <= c.wy0 + a.win_ph - 1 && x0 >= c.wx0 && x0 + 1 <= c.wx0 + a.win_pw - 1;
+          const uint32_t woff16 = (uint32_t)((yc - c.wy0) * a.win_pw + (xc - c.wx0)) * 8u;
+          e.meta = (inside ? (woff16 | WIN_IN) : 0u) | (ddx ? WIN_DX : 0u) | (ddy ? WIN_DY : 0u);
+          const float w00 = (y0ok && x0ok) ? hy * hx * m : 0.f, w01 = (y0ok && x1ok) ? hy * lx * m : 0.f;
+          const float w10 = (y1ok && x0ok) ? ly * hx * m : 0.f, w11 = (y1ok && x1ok) ? ly * lx * m : 0.f;
+          const __nv_bfloat162 wa = __floats2bfloat162_rn(w00, w01), wb = __floats2bfloat162_rn(w10, w11);
+          e.w01 = *reinterpret_cast<const uint32_t*>(&wa);
+          e.w23 = *reinterpret_cast<const uint32_t*>(&wb);
+        }
+      }
+      return e;
+    };
+
+    if (n_my > 0) {
+      if (tid == 0) { issue_window(0); if (n_units > 1) issue_window(1); }
+      // table of the first tile: every thread builds the taps of its parity
+      {
+        const RowCtx c = row_ctx((int)blockIdx.x);
+        for (int tap = thalf; tap < 9; tap += 2) {
+          float dy = 0.f, dx = 0.f, m = 0.f;
+          if (c.ok) { dy = __ldg(c.om + 2 * tap); dx = __ldg(c.om + 2 * tap + 1); m = __ldg(c.om + 18 + tap); }
+          tabs[tap * TC_BM + trow] = make_entry(c, tap, dy, dx, m);
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    int s = 0;
+    for (int t = 0; t < n_my; ++t) {
+      const DcnWinEntry* tab_cur = tabs + (t & 1) * 9 * TC_BM;
+      DcnWinEntry* tab_nxt = tabs + ((t + 1) & 1) * 9 * TC_BM;
+      const bool have_next = t + 1 < n_my;
+      const RowCtx cn = row_ctx((int)blockIdx.x + (t + 1) * G);          // harmless when there is no next tile (ok = false)
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int u = t * nchunks + ch;
+        const uint32_t s_win = sWin + (uint32_t)(u & 1) * win_stride;
+        mbar_wait(win_full(u & 1), (uint32_t)(u >> 1) & 1u);
+        for (int tap = 0; tap < 9; ++tap, ++s) {
+          // next tile's record of this tap: its three `om` floats are requested now and consumed after the slice
+          const bool build = have_next && ch == 0 && (tap & 1) == thalf;
+          float ndy = 0.f, ndx = 0.f, nm = 0.f;
+          if (build && cn.ok) { ndy = __ldg(cn.om + 2 * tap); ndx = __ldg(cn.om + 2 * tap + 1); nm = __ldg(cn.om + 18 + tap); }
+          const int stage = s % DP_SA;
+          const uint32_t ph = (uint32_t)(s / DP_SA) & 1u;
+          mbar_wait(empty_bar(stage), ph ^ 1u);
+          if (tid == 0) {
+            mbar_expect_tx(full_bar(stage), b_tile_bytes);
+            bulk_g2s(sB + stage * b_tile_bytes, a.w + (size_t)(ch * 9 + tap) * a.n_tile * TC_BK, b_tile_bytes, full_bar(stage));
+          }
+          const DcnWinEntry* tab = tab_cur + tap * TC_BM + r0;
+          uint4 e4[TC_NROW], v[TC_NROW][4];
+#pragma unroll
+          for (int i = 0; i < TC_NROW; ++i) e4[i] = *reinterpret_cast<const uint4*>(&tab[32 * i]);
+#pragma unroll
+          for (int i = 0; i < TC_NROW; ++i) {
+            const uint32_t meta = e4[i].y;
+            if (meta & WIN_IN) {
+              const uint32_t base = s_win + ((meta & 0xffffu) << 4) + (uint32_t)(q << 4);
+              const uint32_t dx = (meta & WIN_DX) ? 128u : 0u, dy = (meta & WIN_DY) ? pitch : 0u;
+              v[i][0] = lds16(base); v[i][1] = lds16(base + dx);
+              v[i][2] = lds16(base + dy); v[i][3] = lds16(base + dy + dx);
+            } else {
+              const __nv_bfloat16* p00 = a.x + ((int)e4[i].x + (ch << 6) + (q << 3));
+              const int dx = (meta & WIN_DX) ? gdx : 0, dy = (meta & WIN_DY) ? gdy : 0;
+              v[i][0] = ldg_nc16(p00); v[i][1] = ldg_nc16(p00 + dx);
+              v[i][2] = ldg_nc16(p00 + dy); v[i][3] = ldg_nc16(p00 + dy + dx);
+            }
+          }
+          const uint32_t dst = sA + stage * A_STAGE_BYTES + (uint32_t)r0 * 128u + swz;
+#pragma unroll
+          for (int i = 0; i < TC_NROW; ++i) {
+            const uint32_t w0 = __byte_perm(e4[i].z, 0, 0x1010), w1 = __byte_perm(e4[i].z, 0, 0x3232);
+            const uint32_t w2 = __byte_perm(e4[i].w, 0, 0x1010), w3 = __byte_perm(e4[i].w, 0, 0x3232);
+            uint4 o;
+            o.x = bmul2(v[i][0].x, w0); o.y = bmul2(v[i][0].y, w0); o.z = bmul2(v[i][0].z, w0); o.w = bmul2(v[i][0].w, w0);
+            o.x = bfma2(v[i][1].x, w1, o.x); o.y = bfma2(v[i][1].y, w1, o.y); o.z = bfma2(v[i][1].z, w1, o.z); o.w = bfma2(v[i][1].w, w1, o.w);
+            o.x = bfma2(v[i][2].x, w2, o.x); o.y = bfma2(v[i][2].y, w2, o.y); o.z = bfma2(v[i][2].z, w2, o.z); o.w = bfma2(v[i][2].w, w2, o.w);
+            o.x = bfma2(v[i][3].x, w3, o.x); o.y = bfma2(v[i][3].y, w3, o.y); o.z = bfma2(v[i][3].z, w3, o.z); o.w = bfma2(v[i][3].w, w3, o.w);
+            sts16(dst + i * 4096u, o);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full_bar(stage));
+          if (build) tab_nxt[tap * TC_BM + trow] = make_entry(cn, tap, ndy, ndx, nm);
+        }
+        // every producer is done with this unit's window (and, on chunk 0, with its share of the next table)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (tid == 0 && u + 2 < n_units) issue_window(u + 2);
+      }
+    }
+  } else if (warp == 8) {
+    // ======================================= MMA issuer =======================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(a.n_tile);
+      int s = 0;
+      for (int t = 0; t < n_my; ++t) {
+        const int ai = t & 1;
+        mbar_wait(acc_empty(ai), ((uint32_t)(t >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ai * a.n_tile);
+        for (int sl = 0; sl < 9 * nchunks; ++sl, ++s) {
+          const int stage = s % DP_SA;
+          const uint32_t ph = (uint32_t)(s / DP_SA) & 1u;
+          mbar_wait(full_bar(stage), ph);
+          tc_fence_after();
+          const uint64_t ad = make_sdesc(sA + stage * A_STAGE_BYTES);
+          const uint64_t bd = make_sdesc(sB + stage * b_tile_bytes);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            tc_mma(d_tmem, ad + 2ull * k, bd + 2ull * k, idesc, (sl > 0 || k > 0) ? 1u : 0u);
+          tc_commit(empty_bar(stage));
+        }
+        tc_commit(acc_full(ai));
+      }
+    }
+  } else {
+    // ======================================= epilogue warps 9..12 =======================================
+    const int wq = warp & 3;                          // TMEM lane quarter this warp may read (warp id % 4)
+    const int row = wq * 32 + lane;
+    for (int t = 0; t < n_my; ++t) {
+      const int ai = t & 1;
+      int b, ty, tx;
+      dp_tile_origin(a, (int)blockIdx.x + t * G, b, ty, tx);
+      const int oy = ty * 8 + (row >> 4), ox = tx * 16 + (row & 15);
+      const bool p_ok = oy < g.OH && ox < g.OW;
+      const size_t p = ((size_t)b * g.OH + oy) * g.OW + ox;
+      mbar_wait(acc_full(ai), (uint32_t)(t >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(ai * a.n_tile);
+      for (int col = 0; col < a.n_tile; col += 16) {
+        uint32_t r[16];
+        tc_ld16(t_lane + (uint32_t)col, r);
+        if (!p_ok || col >= g.C_out) continue;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        if (a.shift) {
+          const float4* sh4 = reinterpret_cast<const float4*>(a.shift + col);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 sh = __ldg(sh4 + j4);
+            v[4 * j4] += sh.x; v[4 * j4 + 1] += sh.y; v[4 * j4 + 2] += sh.z; v[4 * j4 + 3] += sh.w;
+          }
+        }
+        if (g.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        uint4 oa, ob;
+        __nv_bfloat162* pa = reinterpret_cast<__nv_bfloat162*>(&oa);
+        __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&ob);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          pa[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+          pb[j] = __floats2bfloat162_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
+        }
+        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + p * g.ld_out + col);
+        op[0] = oa; op[1] = ob;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(ai));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols) : "memory");
+  }
+}
+
 typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1025,6 +1309,33 @@ int conv_forward_tc(const ct_conv_desc* d, cudaStream_t st) {
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(CT_ERR_CUDA, "conv_tc: cuTensorMapEncodeTiled failed%s (%ld)", "", (long)cr);
+  }
+  static const int persist_env = getenv("CTB_DCN_PERSIST") ? atoi(getenv("CTB_DCN_PERSIST")) : 0;   // off until validated on the B200
+  if (win && persist_env && n_tiles == 1 && g.out_mode == CT_OUT_NHWC && d->residual == nullptr && g.C_out % 16 == 0 &&
+      g.C_out == n_tile && ((uintptr_t)d->shift & 15) == 0) {
+    // persistent form: one CTA per SM, two windows + two tables + two accumulators (see dcn_persist_kernel)
+    const size_t win_stride = ((size_t)a.win_bytes + 127) & ~(size_t)127;
+    const size_t psmem = (size_t)DP_SA * (A_STAGE_BYTES + n_tile * 128) + 2 * win_stride + 2 * 9 * TC_BM * sizeof(DcnWinEntry) +
+                         8 * (2 * DP_SA + 6) + 16 + 1024;
+    if (psmem <= 227 * 1024) {
+      int cols2 = 32;
+      while (cols2 < 2 * n_tile) cols2 <<= 1;
+      a.tmem_cols = cols2;
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      static thread_local unsigned long long pattr_mask = 0;
+      static thread_local int sms_of[64] = {0};
+      if (dev >= 64 || !((pattr_mask >> dev) & 1ull)) {
+        CT_CUDA_OK(cudaFuncSetAttribute(dcn_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (dev < 64) { pattr_mask |= 1ull << dev; sms_of[dev] = sms; }
+      } else {
+        sms = sms_of[dev];
+      }
+      const int pgrid = m_tiles < sms ? m_tiles : sms;
+      CT_CUDA_OK(launch_kernel(dcn_persist_kernel, dim3(pgrid), dim3(DP_THREADS), psmem, st, true, a, m_tiles, tmap));
+      return after_launch();
+    }
   }
   dim3 grid(m_tiles, n_tiles);
   if (x3) CT_CUDA_OK(launch_kernel(conv_tc_kernel<true>, grid, dim3(TC_THREADS), smem, st, true, a, tmap));

@@ -76,7 +76,8 @@ DCN_ENGINES = [ENGINES[0], ENGINES[2], ENGINES[2] + ('win',), ENGINES[3]]
 
 @pytest.mark.parametrize('eng', DCN_ENGINES, ids=['simt_f32', 'tcgen05', 'tcgen05_window', 'tcgen05_x3'])
 @pytest.mark.parametrize('shape', [(1, 64, 64, 24, 40), (2, 128, 64, 16, 16), (1, 256, 256, 8, 12),
-                                   (1, 512, 256, 4, 6), (1, 64, 64, 5, 7), (2, 64, 64, 24, 32), (3, 64, 128, 40, 56)])
+                                   (1, 512, 256, 4, 6), (1, 64, 64, 5, 7), (2, 64, 64, 24, 32), (3, 64, 128, 40, 56),
+                                   (4, 64, 64, 64, 96), (4, 128, 64, 64, 96)])     # > 148 patches: several tiles per persistent CTA
 def test_dcn_v2(eng, shape):
   """Offset/mask conv + modulated deformable conv; large offsets push samples across and beyond the
   border (zero padding, partial bilinear weights) and, for the shared-memory-window variant (CT_A_DCN_WIN), beyond
