@@ -906,9 +906,19 @@ conv_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
 //   * the sampling table of tile t+1 is built by the producers one tap per slice while they sample tile t
 //     (its `om` values fetched one slice ahead), into the other of two table buffers;
 //   * two TMEM accumulators: four dedicated epilogue warps drain tile t while the producers / MMA work on tile t+1.
-// Warps 0-7 producers (sampling + table + B copies + window TMA), warp 8 MMA issuer, warps 9-12 epilogue.
+//   * the window is requested ROW BY ROW, two rows per slice of the previous unit: one 43 KB request occupied the TMA
+//     unit for ~5000 cycles and the per-slice weight copies queued behind it (a 5000-cycle bubble at every tile
+//     boundary in the first version of this kernel, profiles/r02_tc_trace_persist.txt).
+//   * every TMA request (weight tile per slice, window rows) is issued by a DEDICATED warp: issuing a bulk copy costs the
+//     issuing thread hundreds of cycles, and with the requests on producer thread 0 its warp was the slowest of every
+//     slice (A written 1700 cycles after the stage was acquired, fine-grained trace in profiles/r02_tc_trace_persist.txt).
+// Warps 0-15 producers (sampling + table), warp 16 MMA issuer, warps 17-20 epilogue, warp 21 TMA issuer.
 // =====================================================================================================================
-constexpr int DP_THREADS = 416;
+constexpr int DP_PWARPS = 16;            // producer warps: a slice is a latency chain per warp (table LDS -> 16 LDS -> blend ->
+                                         // STS -> fence -> arrive, ~1100-1500 cycles with 4 rows per thread): 16 warps x 2 rows
+constexpr int DP_PRODUCERS = DP_PWARPS * 32;
+constexpr int DP_NROW = TC_BM * 8 / DP_PRODUCERS;     // A-tile rows per producer thread per K slice (2)
+constexpr int DP_THREADS = DP_PRODUCERS + 32 + 128 + 32 + 128;   // + MMA warp + 4 epilogue warps + TMA warp + 4 table warps
 constexpr int DP_SA = 3;                 // A/B stages
 
 __device__ __forceinline__ void dp_tile_origin(const TcArgs& a, int tile, int& b, int& ty, int& tx) {
@@ -940,15 +950,21 @@ dcn_persist_kernel(const TcArgs a, const int tiles_total, const __grid_constant_
   auto win_full = [&](int i) { return bars + 8u * (2 * DP_SA + i); };
   auto acc_full = [&](int i) { return bars + 8u * (2 * DP_SA + 2 + i); };
   auto acc_empty = [&](int i) { return bars + 8u * (2 * DP_SA + 4 + i); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + off_bar + 8 * (2 * DP_SA + 6));
+  auto win_empty = [&](int i) { return bars + 8u * (2 * DP_SA + 6 + i); };
+  auto tab_full = [&](int i) { return bars + 8u * (2 * DP_SA + 8 + i); };
+  auto tab_empty = [&](int i) { return bars + 8u * (2 * DP_SA + 10 + i); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + off_bar + 8 * (2 * DP_SA + 12));
 
   pdl_trigger();
   if (tid == 0) {
-    for (int s = 0; s < DP_SA; ++s) { mbar_init(full_bar(s), TC_PRODUCERS / 32); mbar_init(empty_bar(s), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(win_full(i), 1); mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 4); }
+    for (int s = 0; s < DP_SA; ++s) { mbar_init(full_bar(s), DP_PWARPS + 1); mbar_init(empty_bar(s), 1); }   // 16 producer warps + the TMA warp's expect_tx arrival
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(win_full(i), 1); mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 4); mbar_init(win_empty(i), DP_PWARPS);
+      mbar_init(tab_full(i), 4); mbar_init(tab_empty(i), DP_PWARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == DP_PWARPS) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
                  "r"((uint32_t)a.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -966,102 +982,34 @@ dcn_persist_kernel(const TcArgs a, const int tiles_total, const __grid_constant_
   if ((int)blockIdx.x < tiles_total) n_my = (tiles_total - 1 - (int)blockIdx.x) / G + 1;
   const int n_units = n_my * nchunks;
 
-  if (warp < 8) {
+  if (warp < DP_PWARPS) {
     // ======================================= producers =======================================
-    const int q = tid & 7, r0 = tid >> 3;
+    const int q = tid & 7, r0 = tid >> 3;                                // rows r0 + 64 i, i < DP_NROW
     const uint32_t swz = (uint32_t)((q ^ (r0 & 7)) << 4);
-    const int trow = tid & (TC_BM - 1), thalf = tid >> 7;                // table: row, tap parity this thread builds
     const uint32_t pitch = (uint32_t)a.win_pw * 128u;
     const int gdx = g.ld_in, gdy = g.W * g.ld_in;
-
-    auto issue_window = [&](int u) {                                     // tid 0 only
-      const int t = u / nchunks, ch = u - t * nchunks;
-      int b, ty, tx;
-      dp_tile_origin(a, (int)blockIdx.x + t * G, b, ty, tx);
-      mbar_arrive_expect_tx(win_full(u & 1), a.win_bytes);
-      tma_4d(sWin + (uint32_t)(u & 1) * win_stride, &tmap, ch << 6, tx * 16 - 1 - a.win_m, ty * 8 - 1 - a.win_m, b,
-             win_full(u & 1));
-    };
-    // per-tile constants of the row this thread builds records for
-    struct RowCtx { const float* om; int oy, ox, img, wy0, wx0; bool ok; };
-    auto row_ctx = [&](int tile) -> RowCtx {
-      RowCtx c;
-      int b, ty, tx;
-      dp_tile_origin(a, tile, b, ty, tx);
-      c.oy = ty * 8 + (trow >> 4); c.ox = tx * 16 + (trow & 15);
-      c.ok = tile < tiles_total && c.oy < g.OH && c.ox < g.OW;
-      c.img = b * g.H * g.W;
-      c.wy0 = ty * 8 - 1 - a.win_m; c.wx0 = tx * 16 - 1 - a.win_m;
-      c.om = a.om + (size_t)((b * g.OH + c.oy) * g.OW + c.ox) * g.ld_om;
-      return c;
-    };
-    auto make_entry = [&](const RowCtx& c, int tap, float dy, float dx, float m) -> DcnWinEntry {
-      DcnWinEntry e; e.goff = 0; e.meta = WIN_IN; e.w01 = 0u; e.w23 = 0u;
-      if (c.ok) {
-        const float py = (float)(c.oy - 1 + tap / 3) + dy;
-        const float px = (float)(c.ox - 1 + tap % 3) + dx;
-        if (py > -1.f && py < (float)g.H && px > -1.f && px < (float)g.W) {
-          const float y0f = floorf(py), x0f = floorf(px);
-          const int y0 = (int)y0f, x0 = (int)x0f;
-          const float ly = py - y0f, lx = px - x0f, hy = 1.f - ly, hx = 1.f - lx;
-          const bool y0ok = y0 >= 0, y1ok = y0 + 1 <= g.H - 1, x0ok = x0 >= 0, x1ok = x0 + 1 <= g.W - 1;
-          const int yc = max(y0, 0), xc = max(x0, 0);
-          e.goff = (c.img + yc * g.W + xc) * g.ld_in;
-          const bool ddx = x0ok && x1ok, ddy = y0ok && y1ok;
-          const bool inside = y0 >= c.wy0 && y0 + 1 <= c.wy0 + a.win_ph - 1 && x0 >= c.wx0 && x0 + 1 <= c.wx0 + a.win_pw - 1;
-          const uint32_t woff16 = (uint32_t)((yc - c.wy0) * a.win_pw + (xc - c.wx0)) * 8u;
-          e.meta = (inside ? (woff16 | WIN_IN) : 0u) | (ddx ? WIN_DX : 0u) | (ddy ? WIN_DY : 0u);
-          const float w00 = (y0ok && x0ok) ? hy * hx * m : 0.f, w01 = (y0ok && x1ok) ? hy * lx * m : 0.f;
-          const float w10 = (y1ok && x0ok) ? ly * hx * m : 0.f, w11 = (y1ok && x1ok) ? ly * lx * m : 0.f;
-          const __nv_bfloat162 wa = __floats2bfloat162_rn(w00, w01), wb = __floats2bfloat162_rn(w10, w11);
-          e.w01 = *reinterpret_cast<const uint32_t*>(&wa);
-          e.w23 = *reinterpret_cast<const uint32_t*>(&wb);
-        }
-      }
-      return e;
-    };
-
-    if (n_my > 0) {
-      if (tid == 0) { issue_window(0); if (n_units > 1) issue_window(1); }
-      // table of the first tile: every thread builds the taps of its parity
-      {
-        const RowCtx c = row_ctx((int)blockIdx.x);
-        for (int tap = thalf; tap < 9; tap += 2) {
-          float dy = 0.f, dx = 0.f, m = 0.f;
-          if (c.ok) { dy = __ldg(c.om + 2 * tap); dx = __ldg(c.om + 2 * tap + 1); m = __ldg(c.om + 18 + tap); }
-          tabs[tap * TC_BM + trow] = make_entry(c, tap, dy, dx, m);
-        }
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-    }
+    // Nothing but the slice loop lives here: `fence.proxy.async` compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, and the
+    // MEMBAR waits for every outstanding load of the thread, so a prefetch of the next tile's `om` floats in flight across
+    // it cost the warp a full L2 round trip per slice.  The records are built by the table warps below.
     int s = 0;
     for (int t = 0; t < n_my; ++t) {
       const DcnWinEntry* tab_cur = tabs + (t & 1) * 9 * TC_BM;
-      DcnWinEntry* tab_nxt = tabs + ((t + 1) & 1) * 9 * TC_BM;
-      const bool have_next = t + 1 < n_my;
-      const RowCtx cn = row_ctx((int)blockIdx.x + (t + 1) * G);          // harmless when there is no next tile (ok = false)
+      mbar_wait(tab_full(t & 1), (uint32_t)(t >> 1) & 1u);
       for (int ch = 0; ch < nchunks; ++ch) {
         const int u = t * nchunks + ch;
         const uint32_t s_win = sWin + (uint32_t)(u & 1) * win_stride;
         mbar_wait(win_full(u & 1), (uint32_t)(u >> 1) & 1u);
         for (int tap = 0; tap < 9; ++tap, ++s) {
-          // next tile's record of this tap: its three `om` floats are requested now and consumed after the slice
-          const bool build = have_next && ch == 0 && (tap & 1) == thalf;
-          float ndy = 0.f, ndx = 0.f, nm = 0.f;
-          if (build && cn.ok) { ndy = __ldg(cn.om + 2 * tap); ndx = __ldg(cn.om + 2 * tap + 1); nm = __ldg(cn.om + 18 + tap); }
           const int stage = s % DP_SA;
           const uint32_t ph = (uint32_t)(s / DP_SA) & 1u;
           mbar_wait(empty_bar(stage), ph ^ 1u);
-          if (tid == 0) {
-            mbar_expect_tx(full_bar(stage), b_tile_bytes);
-            bulk_g2s(sB + stage * b_tile_bytes, a.w + (size_t)(ch * 9 + tap) * a.n_tile * TC_BK, b_tile_bytes, full_bar(stage));
-          }
+          if (tid == 0 && s < 60) tc_stamp(16 + 4 * s);
           const DcnWinEntry* tab = tab_cur + tap * TC_BM + r0;
-          uint4 e4[TC_NROW], v[TC_NROW][4];
+          uint4 e4[DP_NROW], v[DP_NROW][4];
 #pragma unroll
-          for (int i = 0; i < TC_NROW; ++i) e4[i] = *reinterpret_cast<const uint4*>(&tab[32 * i]);
+          for (int i = 0; i < DP_NROW; ++i) e4[i] = *reinterpret_cast<const uint4*>(&tab[64 * i]);
 #pragma unroll
-          for (int i = 0; i < TC_NROW; ++i) {
+          for (int i = 0; i < DP_NROW; ++i) {
             const uint32_t meta = e4[i].y;
             if (meta & WIN_IN) {
               const uint32_t base = s_win + ((meta & 0xffffu) << 4) + (uint32_t)(q << 4);
@@ -1077,7 +1025,7 @@ dcn_persist_kernel(const TcArgs a, const int tiles_total, const __grid_constant_
           }
           const uint32_t dst = sA + stage * A_STAGE_BYTES + (uint32_t)r0 * 128u + swz;
 #pragma unroll
-          for (int i = 0; i < TC_NROW; ++i) {
+          for (int i = 0; i < DP_NROW; ++i) {
             const uint32_t w0 = __byte_perm(e4[i].z, 0, 0x1010), w1 = __byte_perm(e4[i].z, 0, 0x3232);
             const uint32_t w2 = __byte_perm(e4[i].w, 0, 0x1010), w3 = __byte_perm(e4[i].w, 0, 0x3232);
             uint4 o;
@@ -1085,19 +1033,109 @@ dcn_persist_kernel(const TcArgs a, const int tiles_total, const __grid_constant_
             o.x = bfma2(v[i][1].x, w1, o.x); o.y = bfma2(v[i][1].y, w1, o.y); o.z = bfma2(v[i][1].z, w1, o.z); o.w = bfma2(v[i][1].w, w1, o.w);
             o.x = bfma2(v[i][2].x, w2, o.x); o.y = bfma2(v[i][2].y, w2, o.y); o.z = bfma2(v[i][2].z, w2, o.z); o.w = bfma2(v[i][2].w, w2, o.w);
             o.x = bfma2(v[i][3].x, w3, o.x); o.y = bfma2(v[i][3].y, w3, o.y); o.z = bfma2(v[i][3].z, w3, o.z); o.w = bfma2(v[i][3].w, w3, o.w);
-            sts16(dst + i * 4096u, o);
+            sts16(dst + i * 8192u, o);
           }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(full_bar(stage));
-          if (build) tab_nxt[tap * TC_BM + trow] = make_entry(cn, tap, ndy, ndx, nm);
+          if (tid == 0 && s < 60) tc_stamp(16 + 4 * s + 1);
         }
-        // every producer is done with this unit's window (and, on chunk 0, with its share of the next table)
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (tid == 0 && u + 2 < n_units) issue_window(u + 2);
+        if (lane == 0) mbar_arrive(win_empty(u & 1));                    // this warp is done with the unit's window
+      }
+      if (lane == 0) mbar_arrive(tab_empty(t & 1));                      // ... and with the tile's table
+    }
+  } else if (warp >= DP_PWARPS + 6) {
+    // ======================================= table warps: one thread per A-tile row =======================================
+    // Records of tile t into table t & 1, up to two tiles ahead of the producers.  A record is (global offset of corner 00,
+    // window offset | flags, 4 bf16 corner weights with the modulation mask folded in); see conv_tc_kernel's window path.
+    const int trow = tid - (DP_PWARPS + 6) * 32;
+    for (int t = 0; t < n_my; ++t) {
+      const int tile = (int)blockIdx.x + t * G;
+      int b, ty, tx;
+      dp_tile_origin(a, tile, b, ty, tx);
+      const int oy = ty * 8 + (trow >> 4), ox = tx * 16 + (trow & 15);
+      const bool ok = oy < g.OH && ox < g.OW;
+      const int img = b * g.H * g.W;
+      const int wy0 = ty * 8 - 1 - a.win_m, wx0 = tx * 16 - 1 - a.win_m;
+      float omv[28];
+#pragma unroll
+      for (int j = 0; j < 28; ++j) omv[j] = 0.f;
+      if (ok) {
+        const float4* om4 = reinterpret_cast<const float4*>(a.om + (size_t)((b * g.OH + oy) * g.OW + ox) * g.ld_om);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+          const float4 f = __ldg(om4 + j);
+          omv[4 * j] = f.x; omv[4 * j + 1] = f.y; omv[4 * j + 2] = f.z; omv[4 * j + 3] = f.w;
+        }
+      }
+      if (t >= 2) mbar_wait(tab_empty(t & 1), (uint32_t)((t - 2) >> 1) & 1u);
+      DcnWinEntry* tab = tabs + (t & 1) * 9 * TC_BM + trow;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        DcnWinEntry e; e.goff = 0; e.meta = WIN_IN; e.w01 = 0u; e.w23 = 0u;
+        if (ok) {
+          const float py = (float)(oy - 1 + tap / 3) + omv[2 * tap];
+          const float px = (float)(ox - 1 + tap % 3) + omv[2 * tap + 1];
+          const float m = omv[18 + tap];
+          if (py > -1.f && py < (float)g.H && px > -1.f && px < (float)g.W) {
+            const float y0f = floorf(py), x0f = floorf(px);
+            const int y0 = (int)y0f, x0 = (int)x0f;
+            const float ly = py - y0f, lx = px - x0f, hy = 1.f - ly, hx = 1.f - lx;
+            const bool y0ok = y0 >= 0, y1ok = y0 + 1 <= g.H - 1, x0ok = x0 >= 0, x1ok = x0 + 1 <= g.W - 1;
+            const int yc = max(y0, 0), xc = max(x0, 0);
+            e.goff = (img + yc * g.W + xc) * g.ld_in;
+            const bool ddx = x0ok && x1ok, ddy = y0ok && y1ok;
+            const bool inside = y0 >= wy0 && y0 + 1 <= wy0 + a.win_ph - 1 && x0 >= wx0 && x0 + 1 <= wx0 + a.win_pw - 1;
+            const uint32_t woff16 = (uint32_t)((yc - wy0) * a.win_pw + (xc - wx0)) * 8u;
+            e.meta = (inside ? (woff16 | WIN_IN) : 0u) | (ddx ? WIN_DX : 0u) | (ddy ? WIN_DY : 0u);
+            const float w00 = (y0ok && x0ok) ? hy * hx * m : 0.f, w01 = (y0ok && x1ok) ? hy * lx * m : 0.f;
+            const float w10 = (y1ok && x0ok) ? ly * hx * m : 0.f, w11 = (y1ok && x1ok) ? ly * lx * m : 0.f;
+            const __nv_bfloat162 wa = __floats2bfloat162_rn(w00, w01), wb = __floats2bfloat162_rn(w10, w11);
+            e.w01 = *reinterpret_cast<const uint32_t*>(&wa);
+            e.w23 = *reinterpret_cast<const uint32_t*>(&wb);
+          }
+        }
+        tab[tap * TC_BM] = e;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tab_full(t & 1));
+    }
+  } else if (warp == DP_PWARPS + 5) {
+    // ======================================= TMA issuer =======================================
+    if (lane == 0 && n_my > 0) {
+    // window of unit u, rows [ry0, ry1): one TMA request per row (tid 0 only); the first request arms the barrier
+    auto issue_window_rows = [&](int u, int ry0, int ry1) {
+      const int t = u / nchunks, ch = u - t * nchunks;
+      int b, ty, tx;
+      dp_tile_origin(a, (int)blockIdx.x + t * G, b, ty, tx);
+      if (ry0 == 0) mbar_arrive_expect_tx(win_full(u & 1), a.win_bytes);
+      const uint32_t row_bytes = (uint32_t)a.win_pw * 128u;
+      for (int ry = ry0; ry < ry1 && ry < a.win_ph; ++ry)
+        tma_4d(sWin + (uint32_t)(u & 1) * win_stride + (uint32_t)ry * row_bytes, &tmap, ch << 6, tx * 16 - 1 - a.win_m,
+               ty * 8 - 1 - a.win_m + ry, b, win_full(u & 1));
+    };
+      issue_window_rows(0, 0, a.win_ph);
+      int s = 0;
+      for (int u = 0; u < n_units; ++u) {
+        const int ch = u % nchunks;
+        for (int tap = 0; tap < 9; ++tap, ++s) {
+          const int stage = s % DP_SA;
+          const uint32_t ph = (uint32_t)(s / DP_SA) & 1u;
+          mbar_wait(empty_bar(stage), ph ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), b_tile_bytes);        // the weight tile first: the MMA of this slice waits for it
+          bulk_g2s(sB + stage * b_tile_bytes, a.w + (size_t)(ch * 9 + tap) * a.n_tile * TC_BK, b_tile_bytes, full_bar(stage));
+          // next unit's window into the other buffer, three rows per slice from tap 3 on: issuing a request costs this
+          // thread ~100+ cycles, and 15 of them ahead of the first weight tiles of a unit stalled every tile boundary by
+          // ~4000 cycles.  This warp runs at most DP_SA slices ahead of the producers, so by tap 3 they have released
+          // the buffer (unit u - 1) and the wait below does not block.
+          if (u + 1 < n_units && tap >= 3) {
+            if (tap == 3 && u >= 1) mbar_wait(win_empty((u + 1) & 1), (uint32_t)((u - 1) >> 1) & 1u);
+            issue_window_rows(u + 1, 3 * (tap - 3), 3 * (tap - 3) + 3);
+          }
+        }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == DP_PWARPS) {
     // ======================================= MMA issuer =======================================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(a.n_tile);
@@ -1112,18 +1150,20 @@ dcn_persist_kernel(const TcArgs a, const int tiles_total, const __grid_constant_
           const uint32_t ph = (uint32_t)(s / DP_SA) & 1u;
           mbar_wait(full_bar(stage), ph);
           tc_fence_after();
+          if (s < 60) tc_stamp(16 + 4 * s + 2);
           const uint64_t ad = make_sdesc(sA + stage * A_STAGE_BYTES);
           const uint64_t bd = make_sdesc(sB + stage * b_tile_bytes);
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k)
             tc_mma(d_tmem, ad + 2ull * k, bd + 2ull * k, idesc, (sl > 0 || k > 0) ? 1u : 0u);
           tc_commit(empty_bar(stage));
+          if (s < 60) tc_stamp(16 + 4 * s + 3);
         }
         tc_commit(acc_full(ai));
       }
     }
   } else {
-    // ======================================= epilogue warps 9..12 =======================================
+    // ======================================= epilogue warps 17..20 (warp id % 4 = TMEM lane quarter) =======================================
     const int wq = warp & 3;                          // TMEM lane quarter this warp may read (warp id % 4)
     const int row = wq * 32 + lane;
     for (int t = 0; t < n_my; ++t) {
@@ -1174,7 +1214,7 @@ dcn_persist_kernel(const TcArgs a, const int tiles_total, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == DP_PWARPS) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols) : "memory");
   }
@@ -1316,7 +1356,7 @@ int conv_forward_tc(const ct_conv_desc* d, cudaStream_t st) {
     // persistent form: one CTA per SM, two windows + two tables + two accumulators (see dcn_persist_kernel)
     const size_t win_stride = ((size_t)a.win_bytes + 127) & ~(size_t)127;
     const size_t psmem = (size_t)DP_SA * (A_STAGE_BYTES + n_tile * 128) + 2 * win_stride + 2 * 9 * TC_BM * sizeof(DcnWinEntry) +
-                         8 * (2 * DP_SA + 6) + 16 + 1024;
+                         8 * (2 * DP_SA + 12) + 16 + 1024;
     if (psmem <= 227 * 1024) {
       int cols2 = 32;
       while (cols2 < 2 * n_tile) cols2 <<= 1;
@@ -1333,7 +1373,19 @@ int conv_forward_tc(const ct_conv_desc* d, cudaStream_t st) {
         sms = sms_of[dev];
       }
       const int pgrid = m_tiles < sms ? m_tiles : sms;
-      CT_CUDA_OK(launch_kernel(dcn_persist_kernel, dim3(pgrid), dim3(DP_THREADS), psmem, st, true, a, m_tiles, tmap));
+      CUtensorMap tmap_row;                                  // same tensor, one window ROW per request
+      {
+        TmapEncodeFn enc = tmap_encode_fn();
+        const cuuint64_t dims[4] = {(cuuint64_t)g.C_in, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
+        const cuuint64_t strides[3] = {(cuuint64_t)g.ld_in * 2, (cuuint64_t)g.W * g.ld_in * 2, (cuuint64_t)g.H * g.W * g.ld_in * 2};
+        const cuuint32_t box[4] = {64, (cuuint32_t)a.win_pw, 1, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        const CUresult cr = enc(&tmap_row, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->x), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return fail(CT_ERR_CUDA, "conv_tc: cuTensorMapEncodeTiled failed%s (%ld)", "", (long)cr);
+      }
+      CT_CUDA_OK(launch_kernel(dcn_persist_kernel, dim3(pgrid), dim3(DP_THREADS), psmem, st, true, a, m_tiles, tmap_row));
       return after_launch();
     }
   }

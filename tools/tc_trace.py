@@ -26,6 +26,8 @@ cases = [('DCN 64->64 128x128 B32 global', 32, 64, 64, 128, 128, 3, 1, True, 64)
          ('conv s2 16->32 512x512 (level1)', 16, 16, 32, 512, 512, 3, 2, False, 32)]
 g = torch.Generator().manual_seed(0)
 for (name, B, Cin, Cout, H, W, k, stride, dcn, nt) in cases:
+  if os.environ.get('CTB_TRACE_ONLY') and os.environ['CTB_TRACE_ONLY'] not in name:
+    continue
   x = torch.randn(B, Cin, H, W, generator=g).cuda()
   w = torch.randn(Cout, Cin, k, k, generator=g) * 0.05
   b = torch.zeros(Cout)
@@ -33,6 +35,11 @@ for (name, B, Cin, Cout, H, W, k, stride, dcn, nt) in cases:
   if dcn:
     wo = torch.randn(27, Cin, 3, 3, generator=g) * (0.6 / (Cin * 9) ** 0.5)
     bo = torch.randn(27, generator=g) * (0.7 if B == 32 else 1.5)      # B=32 cases: the benchmark network's offset scale
+    # experiments on what the sampler's time depends on: scale the spread / the per-tap bias of the offsets
+    wo[:18] *= float(os.environ.get('CTB_TRACE_OFF_SPREAD', '1'))
+    bo[:18] *= float(os.environ.get('CTB_TRACE_OFF_BIAS', '1'))
+    if 'CTB_TRACE_OFF_CONST' in os.environ:
+      bo[:18] = float(os.environ['CTB_TRACE_OFF_CONST'])
     om = run_conv(L.CT_ENGINE_TCGEN05, L.CT_BF16, x, wo, bo, 1, relu=False, out_mode=L.CT_OUT_NHWC_F32, sig_from=18, n_tile=32)
     kw.update(a_mode=L.CT_A_DCN_WIN if dcn == 'win' else L.CT_A_DCN, om=om.permute(0, 2, 3, 1).contiguous())
   tr = torch.zeros(256, dtype=torch.int64, device='cuda')
@@ -50,6 +57,15 @@ for (name, B, Cin, Cout, H, W, k, stride, dcn, nt) in cases:
   torch.cuda.synchronize()
   L.check(lib.ct_debug_trace(None))
   t = tr.cpu().numpy().astype(np.int64)
+  if os.environ.get('CTB_DCN_PERSIST') == '1' and dcn == 'win':
+    q = t[16:16 + 240].reshape(60, 4)
+    n = int((q[:, 3] > 0).sum())
+    base = q[0, 0]
+    print('  persistent CTA, per slice (cycles since the first): stage acquired | A written | MMA saw full | MMA committed   [period]')
+    for i in range(min(n, 30)):
+      print('   %2d  %7d %7d %7d %7d   [%d]  A %d  full-after-A %d' % (i, q[i, 0] - base, q[i, 1] - base, q[i, 2] - base, q[i, 3] - base,
+                                                                   (q[i, 1] - q[i - 1, 1]) if i else 0, q[i, 1] - q[i, 0], q[i, 2] - q[i, 1]))
+    continue
   t0 = t[0]
   sl = t[8:]
   n = int((sl > 0).sum())
