@@ -38,9 +38,14 @@ constexpr int HT_W = 8, HT_H = 16;       // output tile (x, y)
 // 0 producer acquired the halo stage, 1 TMA issued, 2 MMA saw the halo, 3 MMA got a free accumulator,
 // 4 MMAs issued + committed, 5 epilogue saw the accumulator, 6 epilogue released it.  Off (nullptr) by default.
 __device__ unsigned long long* g_halo_trace = nullptr;
-__device__ __forceinline__ void h_stamp(int it, int k) {
+// The pointer is read once per thread at kernel entry: the MMA issuing thread is the critical resource of the thin layers
+// and must not pay a dependent load per stamp when tracing is off.
+__device__ __forceinline__ unsigned long long* h_trace_ptr() {
   unsigned long long* t = g_halo_trace;
-  if (t != nullptr && blockIdx.x == 0 && it < 256) t[it * 8 + k] = (unsigned long long)clock64();
+  return (t != nullptr && blockIdx.x == 0) ? t : nullptr;
+}
+__device__ __forceinline__ void h_stamp(unsigned long long* t, int it, int k) {
+  if (t != nullptr && it < 256) t[it * 8 + k] = (unsigned long long)clock64();
 }
 constexpr int H_THREADS = 352;           // 8 epilogue warps + TMA warp + 2 MMA warps
 constexpr int H_EPI_WARPS = 8;
@@ -194,6 +199,7 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
   unsigned char* sm = hsm_dyn + ((1024u - (h_smem_u32(hsm_dyn) & 1023u)) & 1023u);
   const ConvGeom& g = a.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  unsigned long long* const trace = h_trace_ptr();
   const int S = a.halo_stages;
   const uint32_t halo_bytes = (uint32_t)a.planes * a.plane_bytes;
 
@@ -260,7 +266,7 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
         const int s = it % S;
         const uint32_t ph = (uint32_t)(it / S) & 1u;
         h_mbar_wait(halo_empty(s), ph ^ 1u, 1, it);
-        h_stamp(it, 0);
+        h_stamp(trace, it, 0);
         const int b = sp / per_img, r = sp - b * per_img;
         const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
         const int x0 = tx * a.tw - g.pad, y0 = ty * a.th - g.pad;
@@ -273,7 +279,7 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
           for (int p = 0; p < a.planes; ++p)
             h_tma_4d(sH + s * halo_bytes + p * a.plane_bytes, &tmap, p * cstep, x0, y0, b, halo_full(s));
         }
-        h_stamp(it, 1);
+        h_stamp(trace, it, 1);
       }
     }
   } else if (warp == 9 || warp == 10) {
@@ -309,9 +315,9 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
         const int acc = it % NACC;                 // warp `parity` owns accumulators parity, parity + 2
         const uint32_t pa = (uint32_t)(it / NACC) & 1u;
         h_mbar_wait(halo_full(s), ph, 3, it);
-        if (leader) h_stamp(it, 2);
+        if (leader) h_stamp(trace, it, 2);
         h_mbar_wait(tmem_empty(acc), pa ^ 1u, 4, it);
-        if (leader) h_stamp(it, 3);
+        if (leader) h_stamp(trace, it, 3);
         h_fence_after();
         const uint32_t stage16 = ((uint32_t)s * halo_bytes) >> 4;      // start address field stays < 2^14
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.n_tile);
@@ -332,7 +338,7 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
         }
         h_commit_elect(halo_empty(s));
         h_commit_elect(tmem_full(acc));
-        if (leader) h_stamp(it, 4);
+        if (leader) h_stamp(trace, it, 4);
       }
     }
   } else {
@@ -376,7 +382,7 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
       const bool p_ok = oy < g.OH && ox < g.OW;
       const size_t p = ((size_t)b * g.OH + oy) * g.OW + ox;
       h_mbar_wait(tmem_full(acc), pa, 5, it);
-      if (tid == 0) h_stamp(it, 6 - 1);
+      if (tid == 0) h_stamp(trace, it, 6 - 1);
       h_fence_after();
       const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * a.n_tile);
       if (a.sum3) {
@@ -408,7 +414,7 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
         for (int col = chalf * 16; col < a.n_tile; col += 32) {
           uint32_t rr[16];
           h_ld16(t_lane + (uint32_t)col, rr);
-          if (tid == 0 && col == 0) h_stamp(it, 7);
+          if (tid == 0 && col == 0) h_stamp(trace, it, 7);
           const int o0 = n0 + col;
           if (!p_ok || o0 >= g.C_out) continue;
           float v[16];
@@ -496,7 +502,7 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
       h_fence_before();
       __syncwarp();
       if (lane == 0) h_mbar_arrive(tmem_empty(acc));      // one arrival per epilogue warp frees the accumulator
-      if (tid == 0) h_stamp(it, 6);
+      if (tid == 0) h_stamp(trace, it, 6);
     }
   }
 

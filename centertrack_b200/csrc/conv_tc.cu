@@ -79,9 +79,14 @@ __device__ __forceinline__ int tc_pixel(const TcArgs& a, int mt, int r) {
 // Optional timeline of the middle CTA (ct_debug_trace): clock64() stamps -- 0 start, 1 rows set up, 2 DCN table built,
 // 8+s producer warp 0 finished slice s, 4 MMA warp committed, 5 epilogue saw the accumulator, 6 epilogue done.
 __device__ unsigned long long* g_tc_trace = nullptr;
-__device__ __forceinline__ void tc_stamp(int k) {
+// The pointer is read ONCE per thread at kernel entry (tc_trace_ptr): a stamp that re-read the global cost the stamping
+// thread a dependent load per slice even with tracing off.
+__device__ __forceinline__ unsigned long long* tc_trace_ptr() {
   unsigned long long* t = g_tc_trace;
-  if (t != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && k < 256) t[k] = (unsigned long long)clock64();
+  return (t != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0) ? t : nullptr;
+}
+__device__ __forceinline__ void tc_stamp(unsigned long long* t, int k) {
+  if (t != nullptr && k < 256) t[k] = (unsigned long long)clock64();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -256,6 +261,7 @@ conv_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const ConvGeom& g = a.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  unsigned long long* const trace = tc_trace_ptr();
   const int S = a.stages;
   const uint32_t b_tile_bytes = (uint32_t)a.n_tile * 128u;                    // one bf16 weight tile of a K slice
   const uint32_t b_stage_bytes = X3 ? 2u * b_tile_bytes : b_tile_bytes;       // X3: [hi][lo]
@@ -282,7 +288,7 @@ conv_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
   const int mt = blockIdx.x;
   const int nt = blockIdx.y;
   const int n0 = nt * a.n_tile;
-  if (tid == 0) tc_stamp(0);
+  if (tid == 0) tc_stamp(trace, 0);
   pdl_trigger();                       // the next kernel of the stream may start its own prologue now
 
   if (tid == 0) {
@@ -302,7 +308,7 @@ conv_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (tid == 0) tc_stamp(7);
+  if (tid == 0) tc_stamp(trace, 7);
   pdl_wait();                          // everything below reads what the previous kernel wrote
 
   if (warp < 8) {
@@ -349,7 +355,7 @@ conv_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
         while (oy >= g.OH) { oy -= g.OH; ++b; }
       }
     }
-    if (tid == 0) tc_stamp(1);
+    if (tid == 0) tc_stamp(trace, 1);
     int win_x0 = 0, win_y0 = 0, win_b = 0;
     if (win) {
       // window origin of this 8x16 patch: one kernel-halo pixel + the offset margin to the top/left
@@ -417,7 +423,7 @@ conv_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (tid == 0) tc_stamp(2);
+      if (tid == 0) tc_stamp(trace, 2);
     }
     if (a.a_mode == CT_A_DCN) {
       // per (tap,row) sampling records, computed once per CTA (row = tid, threads 0..127)
@@ -460,7 +466,7 @@ conv_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (tid == 0) tc_stamp(2);
+      if (tid == 0) tc_stamp(trace, 2);
     }
     const int cin8 = g.C_in >> 3;
     const int ntaps = g.KH * g.KW;
@@ -520,7 +526,7 @@ conv_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(full_bar(stage));
-          if (tid == 0) tc_stamp(8 + s);
+          if (tid == 0) tc_stamp(trace, 8 + s);
         }
         if (ch + 1 < nchunks) {                       // every producer is done with this chunk's window: refill it
           asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -546,7 +552,7 @@ conv_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(full_bar(stage));
-        if (tid == 0) tc_stamp(8 + s);
+        if (tid == 0) tc_stamp(trace, 8 + s);
       };
       if (a.a_mode == CT_A_DCN) {
         float4 va[2][4][2], vb[2][4][2];
@@ -698,7 +704,7 @@ conv_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(full_bar(stage));      // one arrival per producer warp
-        if (tid == 0) tc_stamp(8 + s);
+        if (tid == 0) tc_stamp(trace, 8 + s);
       }
     } else {
       // Plain convolution gather, register-prefetched three K slices ahead (12 independent 16-byte loads in flight
@@ -734,7 +740,7 @@ conv_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
         __syncwarp();
         if (lane == 0) mbar_arrive(full_bar(stage));      // one arrival per producer warp (256 arrivals on one
                                                           // shared-memory word serialise)
-        if (tid == 0) tc_stamp(8 + s);
+        if (tid == 0) tc_stamp(trace, 8 + s);
       };
       const int KS = a.k_slices;
       uint4 v0[TC_NROW], v1[TC_NROW], v2[TC_NROW];
@@ -752,7 +758,7 @@ conv_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
     // =========================== epilogue ===========================
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    if (tid == 0) tc_stamp(5);
+    if (tid == 0) tc_stamp(trace, 5);
     const int wq = warp & 3, chalf = warp >> 2;      // TMEM lane quarter, column-chunk parity
     const int row = wq * 32 + lane;
     const int p = tc_pixel(a, mt, row);
@@ -883,12 +889,12 @@ conv_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
       tc_commit(empty_bar(stage));     // frees this smem stage when the MMAs above have read it
     }
     tc_commit(tmem_full_bar);           // accumulator complete -> epilogue
-    tc_stamp(4);
+    tc_stamp(trace, 4);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (tid == 0) tc_stamp(6);
+  if (tid == 0) tc_stamp(trace, 6);
   if (warp == 8) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols)
@@ -935,6 +941,7 @@ dcn_persist_kernel(const TcArgs a, const int tiles_total, const __grid_constant_
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const ConvGeom& g = a.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  unsigned long long* const trace = tc_trace_ptr();
   const uint32_t b_tile_bytes = (uint32_t)a.n_tile * 128u;
   const uint32_t win_stride = (a.win_bytes + 127u) & ~127u;
   const uint32_t smem_base = smem_u32(smem);
@@ -1003,7 +1010,7 @@ dcn_persist_kernel(const TcArgs a, const int tiles_total, const __grid_constant_
           const int stage = s % DP_SA;
           const uint32_t ph = (uint32_t)(s / DP_SA) & 1u;
           mbar_wait(empty_bar(stage), ph ^ 1u);
-          if (tid == 0 && s < 60) tc_stamp(16 + 4 * s);
+          if (tid == 0 && s < 60) tc_stamp(trace, 16 + 4 * s);
           const DcnWinEntry* tab = tab_cur + tap * TC_BM + r0;
           uint4 e4[DP_NROW], v[DP_NROW][4];
 #pragma unroll
@@ -1038,7 +1045,7 @@ dcn_persist_kernel(const TcArgs a, const int tiles_total, const __grid_constant_
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(full_bar(stage));
-          if (tid == 0 && s < 60) tc_stamp(16 + 4 * s + 1);
+          if (tid == 0 && s < 60) tc_stamp(trace, 16 + 4 * s + 1);
         }
         if (lane == 0) mbar_arrive(win_empty(u & 1));                    // this warp is done with the unit's window
       }
@@ -1150,14 +1157,14 @@ dcn_persist_kernel(const TcArgs a, const int tiles_total, const __grid_constant_
           const uint32_t ph = (uint32_t)(s / DP_SA) & 1u;
           mbar_wait(full_bar(stage), ph);
           tc_fence_after();
-          if (s < 60) tc_stamp(16 + 4 * s + 2);
+          if (s < 60) tc_stamp(trace, 16 + 4 * s + 2);
           const uint64_t ad = make_sdesc(sA + stage * A_STAGE_BYTES);
           const uint64_t bd = make_sdesc(sB + stage * b_tile_bytes);
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k)
             tc_mma(d_tmem, ad + 2ull * k, bd + 2ull * k, idesc, (sl > 0 || k > 0) ? 1u : 0u);
           tc_commit(empty_bar(stage));
-          if (s < 60) tc_stamp(16 + 4 * s + 3);
+          if (s < 60) tc_stamp(trace, 16 + 4 * s + 3);
         }
         tc_commit(acc_full(ai));
       }
