@@ -1357,7 +1357,7 @@ int conv_forward_tc(const ct_conv_desc* d, cudaStream_t st) {
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(CT_ERR_CUDA, "conv_tc: cuTensorMapEncodeTiled failed%s (%ld)", "", (long)cr);
   }
-  static const int persist_env = getenv("CTB_DCN_PERSIST") ? atoi(getenv("CTB_DCN_PERSIST")) : 0;   // off until validated on the B200
+  static const int persist_env = getenv("CTB_DCN_PERSIST") ? atoi(getenv("CTB_DCN_PERSIST")) : 1;
   if (win && persist_env && n_tiles == 1 && g.out_mode == CT_OUT_NHWC && d->residual == nullptr && g.C_out % 16 == 0 &&
       g.C_out == n_tile && ((uintptr_t)d->shift & 15) == 0) {
     // persistent form: one CTA per SM, two windows + two tables + two accumulators (see dcn_persist_kernel)

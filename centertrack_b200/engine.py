@@ -72,6 +72,8 @@ class DLA34Engine(object):
     self.engine = {'bf16': L.CT_ENGINE_TCGEN05, 'fp32': L.CT_ENGINE_SIMT, 'bf16x3': L.CT_ENGINE_TCGEN05_X3}[precision]
     self.x3 = (precision == "bf16x3")
     self.dcn_window = bool(int(__import__('os').environ.get('CTB_DCN_WINDOW', '1')))
+    # the persistent window kernel (CTB_DCN_PERSIST, default on) also wins on 128 -> 128 at 64x64 (100 vs 124 us)
+    self.dcn_window_all = bool(int(__import__('os').environ.get('CTB_DCN_PERSIST', '1')))
     self.ntile_cap = int(__import__('os').environ.get('CTB_NTILE_CAP', '256'))
     self.depth_scale = float(depth_scale)
     self.has_pre_img = has_pre_img and ('base.pre_img_layer.0.weight' in self.sd)
@@ -217,9 +219,10 @@ class DLA34Engine(object):
                sd[p + '.conv.conv_offset_mask.bias'], om, 3, 1, relu=False,
                out_mode=L.CT_OUT_NHWC_F32, sig_from=18)
     w, shift = self._fold(p + '.conv', p + '.actf.0')
-    # window sampler unless its smem footprint (18 KB table + 43 KB window + stages) would halve the occupancy of a
-    # layer whose N tile is wide and whose input needs two window refills (128 -> 128 at 64x64: measured 155 vs 136 us)
-    if self.engine == L.CT_ENGINE_TCGEN05 and x.C % 64 == 0 and self.dcn_window and not (x.C == 128 and w.shape[0] == 128):
+    # window sampler; without the persistent kernel its smem footprint (18 KB table + 43 KB window + stages) halves the
+    # occupancy of a layer whose N tile is wide and whose input needs two window refills (128 -> 128 at 64x64: 155 vs 136 us)
+    if (self.engine == L.CT_ENGINE_TCGEN05 and x.C % 64 == 0 and self.dcn_window and
+        (self.dcn_window_all or not (x.C == 128 and w.shape[0] == 128))):
       # sample from a TMA-staged shared-memory window; K order = (64-channel chunk, tap, channel)
       nch = x.C // 64
       w_cm = w.reshape(w.shape[0], nch, 64, 3, 3).permute(0, 2, 1, 3, 4).reshape(w.shape[0], 64, nch * 3, 3)
