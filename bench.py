@@ -486,6 +486,9 @@ def main():
                  'peak': peak_hbm, 'unit': 'GB/s', 'frac': dec_gbs / peak_hbm if peak_hbm else None},
       'whole_step_tflops': gflop_per_frame * B / ms_per_step,
       'whole_step_frac': gflop_per_frame * B / ms_per_step / peak_tf if peak_tf else None})
+  if os.environ.get('CTB_BENCH_OPS_FILE'):                   # every op with its engine group, for tools / DESIGN tables
+    with open(os.environ['CTB_BENCH_OPS_FILE'], 'w') as f:
+      json.dump([[name, kind, round(dt * 1000, 1)] for (kind, pl, name), dt in zip(eng.ops, op_ms)], f)
   assert sum_ms <= 1.05 * ms_per_step, 'per-kernel times (%.3f ms) do not add up to the step (%.3f ms)' % (sum_ms, ms_per_step)
 
   # ---------------- parity of the engine that was timed, at the timed shape ----------------

@@ -653,8 +653,9 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
     for (int sdeep = 8; sdeep >= 4; sdeep -= 2)
       if (smem_for(sdeep) <= 220 * 1024 && ctas_for(sdeep) == ctas_for(2)) { stages = sdeep; break; }
   } else {
-    stages = 3;
-    while (stages > 2 && smem_for(stages) > 220 * 1024) --stages;
+    static const int stages1_env = getenv("CTB_HALO_STAGES1") ? atoi(getenv("CTB_HALO_STAGES1")) : 3;
+    stages = stages1_env;
+    while (stages > 2 && (smem_for(stages) > 220 * 1024 || ctas_for(stages) != ctas_for(2))) --stages;
   }
   static const int stages_env = getenv("CTB_HALO_STAGES") ? atoi(getenv("CTB_HALO_STAGES")) : 0;
   if (stages_env) stages = stages_env;

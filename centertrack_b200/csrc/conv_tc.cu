@@ -44,6 +44,9 @@ struct TcArgs {
                                 // 3x3 / bilinear footprints); 0: 128 consecutive pixels in b,y,x order
   int win_m, win_pw, win_ph;    // CT_A_DCN_WIN: offset margin (px) and the staged window (pixels) of one 8x16 patch
   uint32_t win_bytes;           // bytes of one 64-channel window (= TMA box)
+  int fence_mma;                // 1: the generic->async proxy fence is executed by the MMA thread after the full-barrier
+                                // wait instead of by every producer (fence.proxy.async compiles to MEMBAR.ALL.CTA +
+                                // FENCE.VIEW.ASYNC, and the MEMBAR drains the producer's prefetched global loads)
 };
 
 // CT_A_DCN_WIN sampling record (16 bytes): global fall-back offset of the clamped top-left corner (channel 0 of the
@@ -523,7 +526,7 @@ conv_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
             o.x = bfma2(v[i][3].x, w3, o.x); o.y = bfma2(v[i][3].y, w3, o.y); o.z = bfma2(v[i][3].z, w3, o.z); o.w = bfma2(v[i][3].w, w3, o.w);
             sts16(dst + i * 4096u, o);
           }
-          fence_proxy_async();
+          if (!a.fence_mma) fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(full_bar(stage));
           if (tid == 0) tc_stamp(trace, 8 + s);
@@ -549,7 +552,7 @@ conv_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
         return stage;
       };
       auto end_stage = [&](int s, int stage) {
-        fence_proxy_async();
+        if (!a.fence_mma) fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(full_bar(stage));
         if (tid == 0) tc_stamp(trace, 8 + s);
@@ -701,7 +704,7 @@ conv_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
         if (s + 1 < a.k_slices) load_half(ntap, ncq << 3, 0, va);
         blend_half(tap, stage, 1, vb);
         tap = ntap; cq = ncq;
-        fence_proxy_async();
+        if (!a.fence_mma) fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(full_bar(stage));      // one arrival per producer warp
         if (tid == 0) tc_stamp(trace, 8 + s);
@@ -736,7 +739,7 @@ conv_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
         const uint32_t dst = sA + stage * A_STAGE_BYTES + (uint32_t)r0 * 128u + swz;
 #pragma unroll
         for (int i = 0; i < TC_NROW; ++i) sts16(dst + i * 4096u, v[i]);
-        fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        if (!a.fence_mma) fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
         __syncwarp();
         if (lane == 0) mbar_arrive(full_bar(stage));      // one arrival per producer warp (256 arrivals on one
                                                           // shared-memory word serialise)
@@ -869,6 +872,7 @@ conv_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
       const int stage = s % S;
       const uint32_t ph = (uint32_t)(s / S) & 1u;
       mbar_wait(full_bar(stage), ph);
+      if (a.fence_mma) fence_proxy_async();      // the producers' st.shared (acquired through the barrier) -> async proxy
       tc_fence_after();
       const uint64_t ad = make_sdesc(sA + stage * a_stage_bytes);
       const uint64_t bd = make_sdesc(sB + stage * b_stage_bytes);
@@ -1042,7 +1046,7 @@ dcn_persist_kernel(const TcArgs a, const int tiles_total, const __grid_constant_
             o.x = bfma2(v[i][3].x, w3, o.x); o.y = bfma2(v[i][3].y, w3, o.y); o.z = bfma2(v[i][3].z, w3, o.z); o.w = bfma2(v[i][3].w, w3, o.w);
             sts16(dst + i * 8192u, o);
           }
-          fence_proxy_async();
+          if (!a.fence_mma) fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(full_bar(stage));
           if (tid == 0 && s < 60) tc_stamp(trace, 16 + 4 * s + 1);
@@ -1156,6 +1160,7 @@ dcn_persist_kernel(const TcArgs a, const int tiles_total, const __grid_constant_
           const int stage = s % DP_SA;
           const uint32_t ph = (uint32_t)(s / DP_SA) & 1u;
           mbar_wait(full_bar(stage), ph);
+          if (a.fence_mma) fence_proxy_async();
           tc_fence_after();
           if (s < 60) tc_stamp(trace, 16 + 4 * s + 2);
           const uint64_t ad = make_sdesc(sA + stage * A_STAGE_BYTES);
@@ -1241,6 +1246,8 @@ int conv_forward_tc(const ct_conv_desc* d, cudaStream_t st) {
   const bool x3 = d->engine == CT_ENGINE_TCGEN05_X3;     // fp32 activations, bf16 hi/lo split operands
   TcArgs a;
   a.g = make_geom(d);
+  static const int fence_mma_env = getenv("CTB_TC_FENCE_MMA") ? atoi(getenv("CTB_TC_FENCE_MMA")) : 1;
+  a.fence_mma = fence_mma_env;
   const ConvGeom& g = a.g;
   if (g.C_in % 8 != 0 || g.ld_in % 8 != 0)
     return fail(CT_ERR_INVALID, "conv_tc: C_in and ld_in must be multiples of 8%s (%ld,%ld)", "", g.C_in, g.ld_in);
