@@ -15,7 +15,7 @@ SOURCES = ['api.cu', 'conv_simt.cu', 'conv_tc.cu', 'conv_halo.cu', 'elementwise.
 # ---- enums (mirror include/ctb200.h) ----
 CT_F32, CT_BF16 = 0, 1
 CT_A_CONV, CT_A_DCN, CT_A_DCN_WIN = 0, 1, 2
-CT_OUT_NHWC, CT_OUT_NHWC_F32, CT_OUT_NCHW_F32 = 0, 1, 2
+CT_OUT_NHWC, CT_OUT_NHWC_F32, CT_OUT_NCHW_F32, CT_OUT_NHWC_S2D = 0, 1, 2, 3
 CT_HEAD_NONE, CT_HEAD_SIGMOID, CT_HEAD_DEPTH = 0, 1, 2
 CT_ENGINE_SIMT, CT_ENGINE_TCGEN05, CT_ENGINE_TCGEN05_HALO, CT_ENGINE_TCGEN05_X3 = 0, 1, 2, 3
 CT_ROLE_RAW, CT_ROLE_REG, CT_ROLE_WH, CT_ROLE_LTRB, CT_ROLE_LTRB_AMODAL, CT_ROLE_HPS = range(6)

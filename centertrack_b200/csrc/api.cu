@@ -113,10 +113,14 @@ extern "C" int ct_pack_weights(int32_t engine, const float* w, int32_t C_out, in
 extern "C" int ct_conv_forward(const ct_conv_desc* d, void* stream) {
   CT_REQUIRE(d && d->x && d->w && d->out, "null pointer");
   CT_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->C_in > 0 && d->C_out > 0, "bad shape");
-  CT_REQUIRE(d->OH == (d->H + 2 * d->pad - d->KH) / d->stride + 1, "OH inconsistent");
+  // `pad` is the top / left padding; fewer output rows / columns than the symmetric count mean less padding at the
+  // bottom / right (even kernels: 2x2, pad 1 -> taps {-1, 0}, OH = H).  Accepted by the halo engine only.
+  const int oh_full = (d->H + 2 * d->pad - d->KH) / d->stride + 1;
+  CT_REQUIRE(d->OH == oh_full || (d->engine == CT_ENGINE_TCGEN05_HALO && d->OH >= 1 && d->OH < oh_full), "OH inconsistent");
   {
     const int pad_w = d->pad_w1 > 0 ? d->pad_w1 - 1 : d->pad;
-    CT_REQUIRE(d->OW == (d->W + 2 * pad_w - d->KW) / d->stride + 1, "OW inconsistent");
+    const int ow_full = (d->W + 2 * pad_w - d->KW) / d->stride + 1;
+    CT_REQUIRE(d->OW == ow_full || (d->engine == CT_ENGINE_TCGEN05_HALO && d->OW >= 1 && d->OW < ow_full), "OW inconsistent");
     CT_REQUIRE(d->pad_w1 == 0 || d->engine != CT_ENGINE_TCGEN05_HALO, "halo engine: square 'same' kernels only");
   }
   CT_REQUIRE(d->ld_in >= d->C_in, "ld_in < C_in");
@@ -126,6 +130,7 @@ extern "C" int ct_conv_forward(const ct_conv_desc* d, void* stream) {
     CT_REQUIRE(d->a_mode == CT_A_DCN || d->engine == CT_ENGINE_TCGEN05, "CT_A_DCN_WIN: bf16 tcgen05 engine only");
     CT_REQUIRE(d->KH == 3 && d->KW == 3 && d->stride == 1 && d->pad == 1, "DCN is 3x3 s1 p1");
   }
+  CT_REQUIRE(d->out_mode != CT_OUT_NHWC_S2D || d->engine == CT_ENGINE_TCGEN05_HALO, "CT_OUT_NHWC_S2D: halo engine only");
   cudaStream_t st = (cudaStream_t)stream;
   if (d->engine == CT_ENGINE_SIMT) return conv_forward_simt(d, st);
   if (d->engine == CT_ENGINE_TCGEN05) {

@@ -66,6 +66,7 @@ struct HaloArgs {
                                         //    pixel (all C_in channels) per K-major row, hardware swizzle
   int use_base_offset;                  // descriptor base-offset field for shifted (non swizzle-aligned) starts
   int merged_xc;                        // 1: 3-D tensor map with (x, c) merged (C_in == ld_in == 8)
+  int out_s2d;                          // CT_OUT_NHWC_S2D: pixel index remapped in the epilogue (g.out_mode = CT_OUT_NHWC)
   int sum3;                             // != 0: stem epilogue sum_g relu(group g + shift) -> 16 ch; bit g = group present
   uint32_t w_bytes;                     // bytes of one n-tile's weights
   // A-descriptor walk of one work item (all in 16-byte units, warp-uniform): for ky, kx|pair, chunk, kstep
@@ -380,7 +381,8 @@ conv_halo_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
       const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
       const int oy = ty * a.th + gy, ox = tx * a.tw + rx;
       const bool p_ok = oy < g.OH && ox < g.OW;
-      const size_t p = ((size_t)b * g.OH + oy) * g.OW + ox;
+      const size_t p = a.out_s2d ? ((((size_t)b * (g.OH >> 1) + (oy >> 1)) * (g.OW >> 1) + (ox >> 1)) << 2) + (((oy & 1) << 1) | (ox & 1))
+                                 : ((size_t)b * g.OH + oy) * g.OW + ox;
       h_mbar_wait(tmem_full(acc), pa, 5, it);
       if (tid == 0) h_stamp(trace, it, 6 - 1);
       h_fence_after();
@@ -561,6 +563,13 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
   if (((uintptr_t)d->x & 15) || ((uintptr_t)d->w & 15) || ((uintptr_t)d->out & 15))
     return fail(CT_ERR_INVALID, "conv_halo: x/w/out must be 16-byte aligned%s", "");
   a.sum3 = d->epilogue_sum3;
+  a.out_s2d = 0;
+  if (g.out_mode == CT_OUT_NHWC_S2D) {
+    if ((g.OH | g.OW) & 1 || d->residual || a.sum3)
+      return fail(CT_ERR_INVALID, "conv_halo: CT_OUT_NHWC_S2D needs even OH / OW, no residual, no sum3%s", "");
+    a.out_s2d = 1;
+    a.g.out_mode = CT_OUT_NHWC;
+  }
   if (a.sum3 && !(g.C_out == 48 && n_tile == 48 && g.out_mode == CT_OUT_NHWC && d->shift))
     return fail(CT_ERR_INVALID, "conv_halo: sum3 epilogue needs C_out == n_tile == 48, NHWC output, shift%s", "");
   if (g.out_mode == CT_OUT_NHWC && !a.sum3 && (g.C_out % 16 != 0 || g.ld_out % 8 != 0))

@@ -1,6 +1,7 @@
 // Bandwidth-bound pieces of the DLA-34 path: the three 7x7 stems (reference NCHW fp32 inputs in,
 // NHWC activations out), Tree.downsample (2x2 max-pool), IDAUp's depthwise transposed-conv
 // upsample fused with the skip add, and the pre_hm gaussian splat.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace ctb {
@@ -287,6 +288,71 @@ upsample_add_phase_kernel(const T* __restrict__ x, const T* __restrict__ skip, c
   }
 }
 
+// Same operator again, all f*f phases of an input pixel inside ONE warp / CTA: slot (= thread / channel vectors) % f*f is
+// the thread's phase (weights in registers as above), slot / f*f walks the INPUT pixels.  The 2x2 taps of the f*f
+// phases of neighbouring input pixels touch the same 3x3 input lines, which now hit in L1 instead of being fetched
+// from L2 by f*f different CTAs (the phase kernel moved ~6x the output bytes over the L2 -> SM fabric: 64 us for a
+// 151 MB layer), and the f output pixels of a row are adjacent 16-byte-vector groups: one contiguous f*C*2-byte store.
+// Accumulation order = upsample_add_kernel's (bit-identical).
+template <typename T>
+__global__ void __launch_bounds__(256)
+upsample_add_warp_kernel(const T* __restrict__ x, const T* __restrict__ skip, const float* __restrict__ w,
+                         T* __restrict__ out, int B, int H, int W, int C, int f, int ld_in, int ld_skip, int ld_out) {
+  constexpr int V = VecIO<T>::N;
+  const int OW = W * f, OH = H * f, pad = f / 2, k = 2 * f, CV = C / V, ff = f * f;
+  const int slot = threadIdx.x / CV, cg = threadIdx.x - slot * CV, c = cg * V;
+  const int phase = slot % ff, sub = slot / ff;
+  const int py = phase / f, px = phase - py * f;
+  const int dyh = (py + pad) / f, ky0 = (py + pad) - dyh * f;     // taps: (iy = m + dyh, ky0), (iy - 1, ky0 + f)
+  const int dxh = (px + pad) / f, kx0 = (px + pad) - dxh * f;
+  float wr[2][2][V];
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const int ky = ky0 + dy * f, kx = kx0 + dx * f;
+      const float* wp = w + ((size_t)ky * k + kx) * C + c;
+#pragma unroll
+      for (int q = 0; q < V; q += 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(wp + q));
+        wr[dy][dx][q] = t.x; wr[dy][dx][q + 1] = t.y; wr[dy][dx][q + 2] = t.z; wr[dy][dx][q + 3] = t.w;
+      }
+    }
+  const int per_cta = (blockDim.x / CV) / ff;                      // input pixels per CTA per iteration
+  const int total = B * H * W;
+  for (int j = blockIdx.x * per_cta + sub; j < total; j += gridDim.x * per_cta) {
+    const int n = j % W;
+    const int t = j / W;
+    const int m = t % H, b = t / H;
+    const int oy = m * f + py, ox = n * f + px;
+    float acc[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) acc[q] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const int iy = m + dyh - dy;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int ix = n + dxh - dx;
+        if (ix < 0 || ix >= W) continue;
+        float xv[V];
+        VecIO<T>::ld(x + (((size_t)b * H + iy) * W + ix) * ld_in + c, xv);
+#pragma unroll
+        for (int q = 0; q < V; ++q) acc[q] = fmaf(xv[q], wr[dy][dx][q], acc[q]);
+      }
+    }
+    const size_t op = ((size_t)b * OH + oy) * OW + ox;
+    if (skip) {
+      float sv[V];
+      VecIO<T>::ld(skip + op * ld_skip + c, sv);
+#pragma unroll
+      for (int q = 0; q < V; ++q) acc[q] += sv[q];
+    }
+    VecIO<T>::st(out + op * ld_out + c, acc);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // pre_hm splat: draw_umich_gaussian image.py:128-154 (gaussian2D in float64, np.maximum)
 // ------------------------------------------------------------------------------------------
@@ -381,6 +447,21 @@ extern "C" int ct_upsample_add(const void* x, const void* skip, const float* w, 
   const size_t total = (size_t)B * H * f * W * f * (C / vec);
   cudaStream_t st = (cudaStream_t)stream;
   const int cv = C / vec;
+  static const int up_mode = getenv("CTB_UP_MODE") ? atoi(getenv("CTB_UP_MODE")) : 1;
+  if (up_mode == 1 && cv <= 256 && 256 % cv == 0 && (256 / cv) % (f * f) == 0 && (size_t)B * H * W < (1u << 30)) {
+    // all phases of an input pixel in one CTA (L1 reuse of the taps); grid: a few CTAs per SM, grid-stride over pixels
+    const int per_cta = (256 / cv) / (f * f);
+    long gx = ((long)B * H * W + per_cta - 1) / per_cta;
+    if (gx > 148 * 8) gx = 148 * 8;
+    if (dtype == CT_F32)
+      upsample_add_warp_kernel<float><<<(int)gx, 256, 0, st>>>(
+          (const float*)x, (const float*)skip, w, (float*)out, B, H, W, C, f, ld_in, ld_skip, ld_out);
+    else
+      upsample_add_warp_kernel<__nv_bfloat16><<<(int)gx, 256, 0, st>>>(
+          (const __nv_bfloat16*)x, (const __nv_bfloat16*)skip, w, (__nv_bfloat16*)out, B, H, W, C, f,
+          ld_in, ld_skip, ld_out);
+    return after_launch();
+  }
   if (cv <= 256 && 256 % cv == 0 && (size_t)B * H * W < (1u << 30)) {
     // phase kernel: grid.y = f*f phases, grid.x sized so that all phases together fill the GPU a few times over
     const int slots = 256 / cv;

@@ -85,6 +85,8 @@ class DLA34Engine(object):
     self.n_sm = 148
     self.debug_sync = bool(int(__import__('os').environ.get('CTB_DEBUG_SYNC', '0')))
     self.use_halo = use_halo and precision == 'bf16'
+    # level1 as a 2x2 stride-1 halo convolution over level0's output written space-to-depth (see _build)
+    self.s2d_level1 = bool(int(__import__('os').environ.get('CTB_S2D_LEVEL1', '1'))) and self.use_halo
     self._build()
     self.graph = None
 
@@ -136,7 +138,7 @@ class DLA34Engine(object):
 
   def _conv(self, name, x, w, shift, out, k, stride=1, relu=True, residual=None, a_mode=L.CT_A_CONV,
             om=None, out_mode=L.CT_OUT_NHWC, head_act=L.CT_HEAD_NONE, sig_from=1 << 30, c_out=None, sum3=0,
-            w_pack=None):
+            w_pack=None, out_hw=None):
     """Append one conv-like launch.  x: TV; out: TV (NHWC modes) or fp32 tensor (NCHW)."""
     C_in = x.C
     if w.shape[1] != C_in:      # input channels padded (never happens for DLA-34 tensors)
@@ -146,6 +148,8 @@ class DLA34Engine(object):
     pad, pad_w = kh // 2, kw // 2
     OH = (x.H + 2 * pad - kh) // stride + 1
     OW = (x.W + 2 * pad_w - kw) // stride + 1
+    if out_hw is not None:      # even kernels: padding on the top / left only (ctb200.h, OH / OW)
+      OH, OW = out_hw
     P = self.B * OH * OW
     engine = self.engine
     n_tile = self._pick_n_tile(P, C_out) if engine in (L.CT_ENGINE_TCGEN05, L.CT_ENGINE_TCGEN05_X3) else 0
@@ -190,6 +194,10 @@ class DLA34Engine(object):
     elif out_mode == L.CT_OUT_NHWC_F32:
       assert out.shape[:3] == (self.B, OH, OW) and out.dtype == torch.float32
       d.out, d.ld_out = out.data_ptr(), out.shape[-1]
+    elif out_mode == L.CT_OUT_NHWC_S2D:
+      assert engine == L.CT_ENGINE_TCGEN05_HALO and (out.H, out.W, out.C, out.ld) == (OH // 2, OW // 2, 4 * C_out, 4 * C_out)
+      d.out, d.ld_out = out.ptr, C_out
+      self.named[name] = out
     else:
       assert (out.H, out.W) == (OH, OW) and out.C == (16 if sum3 else C_out), (name, out.H, out.W, out.C, OH, OW, C_out)
       d.out, d.ld_out = out.ptr, out.ld
@@ -329,14 +337,32 @@ class DLA34Engine(object):
     self.named['stem'] = x0
 
     # ---- level0 / level1 ----
-    l0 = TV(self._buf(H, W, 16), 0, 16)
-    if self.x3:
-      w0, sh0 = self._fold('base.level0.0', 'base.level0.1')
-      self._conv('base.level0', x0, w0.repeat(1, 3, 1, 1), sh0, l0, 3, 1)
-    else:
-      self._conv_bn('base.level0', x0, 'base.level0.0', 'base.level0.1', l0, 3, 1)
     l1 = TV(self._buf(H // 2, W // 2, 32), 0, 32)
-    self._conv_bn('base.level1', l0, 'base.level1.0', 'base.level1.1', l1, 3, 2)
+    if not (self.s2d_level1 and H % 2 == 0 and W % 2 == 0):
+      l0 = TV(self._buf(H, W, 16), 0, 16)
+      if self.x3:
+        w0, sh0 = self._fold('base.level0.0', 'base.level0.1')
+        self._conv('base.level0', x0, w0.repeat(1, 3, 1, 1), sh0, l0, 3, 1)
+      else:
+        self._conv_bn('base.level0', x0, 'base.level0.0', 'base.level0.1', l0, 3, 1)
+      self._conv_bn('base.level1', l0, 'base.level1.0', 'base.level1.1', l1, 3, 2)
+    else:
+      # level1 (3x3 stride 2, 16 -> 32) as a stride-1 2x2 convolution over the space-to-depth view of level0's output
+      # ([B, H/2, W/2, 4 x 16], written in that layout by level0's epilogue): 64-channel 128-byte rows for the TMA and 16
+      # MMAs per 128 output pixels on the halo engine instead of three latency-bound gather slices (301 -> ~100 us).
+      # Input row 2*oy - 1 + ky = s2d row oy + ty - 1, sub-row sy with (ty, sy) = (0, 1), (1, 0), (1, 1) for ky = 0, 1, 2.
+      l0 = l0s = TV(self._buf(H // 2, W // 2, 64), 0, 64)      # (level0 is below first_level: not an input of DLAUp)
+      w0, sh0 = self._fold('base.level0.0', 'base.level0.1')
+      self._conv('base.level0', x0, w0, sh0, l0s, 3, 1, out_mode=L.CT_OUT_NHWC_S2D)
+      w1, sh1 = self._fold('base.level1.0', 'base.level1.1')
+      w1s = torch.zeros((w1.shape[0], 64, 2, 2), dtype=w1.dtype)
+      tap = ((0, 1), (1, 0), (1, 1))
+      for ky in range(3):
+        for kx in range(3):
+          (ty, sy), (tx, sx) = tap[ky], tap[kx]
+          c0 = (sy * 2 + sx) * 16
+          w1s[:, c0:c0 + 16, ty, tx] = w1[:, :, ky, kx]
+      self._conv('base.level1', l0s, w1s, sh1, l1, 2, 1, out_hw=(H // 2, W // 2))
 
     # ---- level2: Tree(1, 32->64, s2, level_root=False) ----
     h2, w2 = H // 4, W // 4
@@ -542,4 +568,8 @@ class DLA34Engine(object):
 
   def stage(self, name):
     """NCHW fp32 copy of a named intermediate (parity tests)."""
-    return self.named[name].tensor().permute(0, 3, 1, 2).float().contiguous()
+    t = self.named[name].tensor()
+    if name == 'base.level0' and t.shape[-1] == 64:      # written space-to-depth (CT_OUT_NHWC_S2D, see _build)
+      B, h, w, _ = t.shape
+      return t.reshape(B, h, w, 2, 2, 16).permute(0, 5, 1, 3, 2, 4).reshape(B, 16, 2 * h, 2 * w).float().contiguous()
+    return t.permute(0, 3, 1, 2).float().contiguous()

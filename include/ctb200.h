@@ -59,7 +59,11 @@ typedef enum {
 typedef enum {
   CT_OUT_NHWC = 0,       /* out[p*ld_out + o], activation dtype */
   CT_OUT_NHWC_F32 = 1,   /* fp32 NHWC (DCN offset/mask map; sigmoid on channels >= sig_from) */
-  CT_OUT_NCHW_F32 = 2    /* fp32 [B,C_out,H,W] planes (head outputs, reference layout) */
+  CT_OUT_NCHW_F32 = 2,   /* fp32 [B,C_out,H,W] planes (head outputs, reference layout) */
+  CT_OUT_NHWC_S2D = 3    /* CT_OUT_NHWC written space-to-depth: pixel (y, x) lands at pixel (y/2, x/2), channels
+                            [((y&1)*2 + (x&1)) * ld_out, +C_out) of a [B, OH/2, OW/2, 4*ld_out] tensor -- the input
+                            layout of a stride-2 3x3 consumer run as a stride-1 2x2 convolution over 4*C channels
+                            (DLA level0 -> level1).  Halo engine only; OH, OW even; no residual. */
 } ct_out_mode;
 
 typedef enum {           /* per-launch transform applied to the fp32 NCHW head outputs */
@@ -90,7 +94,7 @@ typedef struct {
   int32_t C_out;         /* real output channels */
   int32_t KH, KW, stride, pad;
   int32_t OH, OW;        /* output spatial size */
-  int32_t ld_out;        /* output pixel stride (CT_OUT_NHWC*) */
+  int32_t ld_out;        /* output pixel stride (CT_OUT_NHWC*; CT_OUT_NHWC_S2D: stride of one of the four sub-pixels) */
   int32_t out_mode;      /* ct_out_mode */
   int32_t relu;          /* 1: ReLU after shift (+residual) */
   int32_t ld_res;        /* residual pixel stride (residual may be NULL) */

@@ -20,6 +20,8 @@ def run_conv(engine, dtype, x_nchw, w, bias, stride, relu=True, residual=None, a
   xb[..., ch_off:ch_off + Cin] = x_nchw.permute(0, 2, 3, 1).to(act)
   pad = k // 2
   OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+  if k % 2 == 0:                      # even kernel: padding on the top / left only (taps -k/2 .. k/2-1), 'same' output
+    OH, OW = H, W
   if engine in (L.CT_ENGINE_TCGEN05, L.CT_ENGINE_TCGEN05_HALO, L.CT_ENGINE_TCGEN05_X3) and n_tile == 0:
     cap = 256 if engine == L.CT_ENGINE_TCGEN05 or (engine == L.CT_ENGINE_TCGEN05_X3 and a_mode != L.CT_A_DCN) else 128
     n_tile = min(cap, (O + 15) // 16 * 16)
@@ -54,6 +56,9 @@ def run_conv(engine, dtype, x_nchw, w, bias, stride, relu=True, residual=None, a
   elif out_mode == L.CT_OUT_NHWC_F32:
     out = torch.zeros((B, OH, OW, 32), dtype=torch.float32, device=dev)
     d.out, d.ld_out = out.data_ptr(), 32
+  elif out_mode == L.CT_OUT_NHWC_S2D:
+    out = torch.zeros((B, OH // 2, OW // 2, 4 * O), dtype=act, device=dev)
+    d.out, d.ld_out = out.data_ptr(), O
   else:
     oc = 16 if sum3 else O
     out = torch.zeros((B, OH, OW, oc), dtype=act, device=dev)
@@ -62,6 +67,8 @@ def run_conv(engine, dtype, x_nchw, w, bias, stride, relu=True, residual=None, a
   torch.cuda.synchronize()
   if out_mode == L.CT_OUT_NCHW_F32:
     return out
+  if out_mode == L.CT_OUT_NHWC_S2D:   # undo: [B, OH/2, OW/2, (sy, sx, c)] -> [B, c, OH, OW]
+    return out.reshape(B, OH // 2, OW // 2, 2, 2, O).permute(0, 5, 1, 3, 2, 4).reshape(B, O, OH, OW).float()
   return out.permute(0, 3, 1, 2).float()
 
 

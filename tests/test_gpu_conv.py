@@ -199,6 +199,46 @@ def test_pack_stem_input():
   assert torch.equal(out, ref)
 
 
+def test_halo_even_kernel_and_space_to_depth_output():
+  """The two pieces of level1-as-a-2x2-convolution (engine.py): a 2x2 stride-1 conv padded on the top / left only, and a
+  3x3 conv whose NHWC output is written space-to-depth; then the composition against the 3x3 stride-2 conv itself."""
+  from gpu_helpers import run_conv
+  g = torch.Generator().manual_seed(21)
+  B, H, W = 2, 48, 80
+  x = torch.randn(B, 64, H, W, generator=g)
+  w = torch.randn(32, 64, 2, 2, generator=g) * 0.08
+  b = torch.randn(32, generator=g) * 0.1
+  got = run_conv(L.CT_ENGINE_TCGEN05_HALO, L.CT_BF16, x.cuda(), w, b, 1, True, n_tile=32).cpu()
+  xb, wb = x.bfloat16().float(), w.bfloat16().float()
+  ref = F.relu(F.conv2d(F.pad(xb, (1, 0, 1, 0)), wb, b))
+  assert got.shape == ref.shape
+  assert (got - ref).abs().max() < 2e-2 * max(1.0, float(ref.abs().max()))
+
+  x0 = torch.randn(B, 16, H, W, generator=g)
+  w0 = torch.randn(16, 16, 3, 3, generator=g) * 0.15
+  b0 = torch.randn(16, generator=g) * 0.1
+  plain = run_conv(L.CT_ENGINE_TCGEN05_HALO, L.CT_BF16, x0.cuda(), w0, b0, 1, True, n_tile=16).cpu()
+  s2d = run_conv(L.CT_ENGINE_TCGEN05_HALO, L.CT_BF16, x0.cuda(), w0, b0, 1, True, n_tile=16,
+                 out_mode=L.CT_OUT_NHWC_S2D).cpu()
+  assert torch.equal(plain, s2d)                      # same values, only the layout differs
+
+  # composition: 3x3 stride-2 16 -> 32 == 2x2 stride-1 over the space-to-depth view with the regrouped weights
+  w1 = torch.randn(32, 16, 3, 3, generator=g) * 0.1
+  b1 = torch.randn(32, generator=g) * 0.1
+  w1s = torch.zeros(32, 64, 2, 2)
+  tap = ((0, 1), (1, 0), (1, 1))
+  for ky in range(3):
+    for kx in range(3):
+      (ty, sy), (tx, sx) = tap[ky], tap[kx]
+      w1s[:, (sy * 2 + sx) * 16:(sy * 2 + sx) * 16 + 16, ty, tx] = w1[:, :, ky, kx]
+  xs = plain.reshape(B, 16, H // 2, 2, W // 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(B, 64, H // 2, W // 2)
+  via = run_conv(L.CT_ENGINE_TCGEN05_HALO, L.CT_BF16, xs.cuda(), w1s, b1, 1, True, n_tile=32).cpu()
+  direct = run_conv(L.CT_ENGINE_TCGEN05, L.CT_BF16, plain.cuda(), w1, b1, 2, True).cpu()
+  ref1 = F.relu(F.conv2d(plain, w1.bfloat16().float(), b1, 2, 1))
+  assert (via - ref1).abs().max() < 2e-2 * max(1.0, float(ref1.abs().max()))
+  assert (via - direct).abs().max() < 2e-2 * max(1.0, float(ref1.abs().max()))
+
+
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 def test_maxpool_and_upsample_add(dtype):
   lib = L.lib()
