@@ -146,6 +146,22 @@ template <> struct VecIO<__nv_bfloat16> {
   }
 };
 
+// 16 raw bytes now, conversion at the point of use (keeps several loads in flight without holding their fp32 copies)
+// (asm volatile: the loads keep their program order -- the compiler otherwise sinks the long-latency skip load below the FMAs)
+__device__ __forceinline__ uint4 ld_raw16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void cvt_raw16(const uint4& t, float (&v)[4]) {
+  v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
+}
+__device__ __forceinline__ void cvt_raw16(const uint4& t, float (&v)[8]) {
+  const uint32_t u[4] = {t.x, t.y, t.z, t.w};                     // bf16 -> fp32 is a shift / a mask (exact)
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { v[2 * q] = __uint_as_float(u[q] << 16); v[2 * q + 1] = __uint_as_float(u[q] & 0xffff0000u); }
+}
+
 template <typename T>
 __global__ void maxpool2_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, int W, int C,
                                 int ld_in, int ld_out) {
@@ -318,38 +334,60 @@ upsample_add_warp_kernel(const T* __restrict__ x, const T* __restrict__ skip, co
         wr[dy][dx][q] = t.x; wr[dy][dx][q + 1] = t.y; wr[dy][dx][q + 2] = t.z; wr[dy][dx][q + 3] = t.w;
       }
     }
+  // Index arithmetic is 32-bit and incremental (the host checks that every tensor has < 2^31 elements): (b, m, n) advance
+  // by the constant grid stride with carries instead of two divisions per pixel, and the four taps are constant element
+  // offsets from one base -- the integer work was 4x the 32 FMAs of an output vector (ncu: issue slots 55-60 % busy at
+  // 21 % of the DRAM bandwidth).
   const int per_cta = (blockDim.x / CV) / ff;                      // input pixels per CTA per iteration
   const int total = B * H * W;
-  for (int j = blockIdx.x * per_cta + sub; j < total; j += gridDim.x * per_cta) {
-    const int n = j % W;
-    const int t = j / W;
-    const int m = t % H, b = t / H;
-    const int oy = m * f + py, ox = n * f + px;
+  const int stride = gridDim.x * per_cta;
+  const int s_n = stride % W, s_t = stride / W;                    // stride = s_t * W + s_n, s_t rows (over b, m)
+  int j = blockIdx.x * per_cta + sub;
+  int n = j % W, t = j / W;                                        // t = b * H + m
+  int m = t % H;
+  const int s_m = s_t % H;
+  const int tap_off[2][2] = {{(dyh * W + dxh) * ld_in, (dyh * W + dxh - 1) * ld_in},
+                             {((dyh - 1) * W + dxh) * ld_in, ((dyh - 1) * W + dxh - 1) * ld_in}};
+  const T* xc = x + c;
+  const T* sc = skip ? skip + c : nullptr;
+  T* oc = out + c;
+  for (; j < total; j += stride) {
+    // the four tap loads and the skip load are issued together (no branch between them: a tap outside the image reads
+    // the centre pixel instead and contributes through a zero -- fma(0, w, acc) == acc, so the result is unchanged)
+    const int in_base = (t * W + n) * ld_in;
+    const int op = (t * f + py) * OW + n * f + px;                 // ((b * OH + oy) * OW + ox), oy = m f + py
+    uint4 raw[2][2], raw_s = make_uint4(0, 0, 0, 0);
+    if (sc) raw_s = ld_raw16(sc + op * ld_skip);                   // the DRAM stream first
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const bool ok = (unsigned)(m + dyh - dy) < (unsigned)H && (unsigned)(n + dxh - dx) < (unsigned)W;
+        raw[dy][dx] = ld_raw16(xc + (in_base + (ok ? tap_off[dy][dx] : 0)));
+        if (!ok) raw[dy][dx] = make_uint4(0, 0, 0, 0);             // +0.0 in both dtypes
+      }
     float acc[V];
 #pragma unroll
     for (int q = 0; q < V; ++q) acc[q] = 0.f;
 #pragma unroll
-    for (int dy = 0; dy < 2; ++dy) {
-      const int iy = m + dyh - dy;
-      if (iy < 0 || iy >= H) continue;
+    for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
       for (int dx = 0; dx < 2; ++dx) {
-        const int ix = n + dxh - dx;
-        if (ix < 0 || ix >= W) continue;
         float xv[V];
-        VecIO<T>::ld(x + (((size_t)b * H + iy) * W + ix) * ld_in + c, xv);
+        cvt_raw16(raw[dy][dx], xv);
 #pragma unroll
         for (int q = 0; q < V; ++q) acc[q] = fmaf(xv[q], wr[dy][dx][q], acc[q]);
       }
-    }
-    const size_t op = ((size_t)b * OH + oy) * OW + ox;
-    if (skip) {
+    if (sc) {
       float sv[V];
-      VecIO<T>::ld(skip + op * ld_skip + c, sv);
+      cvt_raw16(raw_s, sv);
 #pragma unroll
       for (int q = 0; q < V; ++q) acc[q] += sv[q];
     }
-    VecIO<T>::st(out + op * ld_out + c, acc);
+    VecIO<T>::st(oc + op * ld_out, acc);
+    n += s_n; t += s_t; m += s_m;
+    if (n >= W) { n -= W; ++t; ++m; }
+    while (m >= H) m -= H;
   }
 }
 
@@ -448,7 +486,8 @@ extern "C" int ct_upsample_add(const void* x, const void* skip, const float* w, 
   cudaStream_t st = (cudaStream_t)stream;
   const int cv = C / vec;
   static const int up_mode = getenv("CTB_UP_MODE") ? atoi(getenv("CTB_UP_MODE")) : 1;
-  if (up_mode == 1 && cv <= 256 && 256 % cv == 0 && (256 / cv) % (f * f) == 0 && (size_t)B * H * W < (1u << 30)) {
+  if (up_mode == 1 && cv <= 256 && 256 % cv == 0 && (256 / cv) % (f * f) == 0 &&
+      (size_t)B * H * f * W * f * (size_t)(ld_out > ld_skip ? ld_out : ld_skip) < (1ull << 31) && (size_t)B * H * W * ld_in < (1ull << 31)) {
     // all phases of an input pixel in one CTA (L1 reuse of the taps); grid: a few CTAs per SM, grid-stride over pixels
     const int per_cta = (256 / cv) / (f * f);
     long gx = ((long)B * H * W + per_cta - 1) / per_cta;
