@@ -173,9 +173,14 @@ def _emit(line):
 # ------------------------------------------------------------------------------------------------------------------
 # per-kernel time inside the step (roofline shares)
 # ------------------------------------------------------------------------------------------------------------------
-def _op_flops(kind, pl, L):
+def _op_flops(kind, pl, L, name=None, eng=None):
+  """ALGORITHMIC flops of the reference layer the launch implements (layers run on a space-to-depth view carry
+  structural zeros in their weights: those MACs are not counted)."""
   if kind != 'conv':
     return 0.0
+  algo = getattr(eng, 'algo_flops', {}).get(name)
+  if algo is not None:
+    return float(algo)
   if pl.epilogue_sum3:
     return 2.0 * pl.B * pl.OH * pl.OW * 16 * 49 * 7            # the three stems: 16 x (3+3+1) x 7x7 MACs/pixel
   return 2.0 * pl.B * pl.OH * pl.OW * pl.C_out * pl.KH * pl.KW * pl.C_in
@@ -434,7 +439,7 @@ def main():
     gname = _op_group(kind, pl, L)
     gr = groups.setdefault(gname, {'ms': 0.0, 'flop': 0.0, 'launches': 0})
     gr['ms'] += dt
-    gr['flop'] += _op_flops(kind, pl, L)
+    gr['flop'] += _op_flops(kind, pl, L, name, eng)
     gr['launches'] += 1
   sum_ms = sum(op_ms) + decode_ms + (tracker_ms or 0.0)
   peak_tf, peak_hbm, peak_src = _peaks()

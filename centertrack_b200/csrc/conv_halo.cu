@@ -565,8 +565,8 @@ int conv_forward_halo(const ct_conv_desc* d, cudaStream_t st) {
   a.sum3 = d->epilogue_sum3;
   a.out_s2d = 0;
   if (g.out_mode == CT_OUT_NHWC_S2D) {
-    if ((g.OH | g.OW) & 1 || d->residual || a.sum3)
-      return fail(CT_ERR_INVALID, "conv_halo: CT_OUT_NHWC_S2D needs even OH / OW, no residual, no sum3%s", "");
+    if ((g.OH | g.OW) & 1 || d->residual)
+      return fail(CT_ERR_INVALID, "conv_halo: CT_OUT_NHWC_S2D needs even OH / OW, no residual%s", "");
     a.out_s2d = 1;
     a.g.out_mode = CT_OUT_NHWC;
   }

@@ -52,6 +52,39 @@ def _pow2_at_least(n):
   return p
 
 
+def s2d_weights_3x3_s1(w):
+  """3x3 stride-1 pad-1 conv [O, I, 3, 3] -> the same operator on the space-to-depth grid: [4 O, 4 I, 3, 3] acting on
+  channels (sy, sx, c) of [B, 4 C, H/2, W/2].  Output sub-pixel sy' reads full-res row 2Y + sy' + ky - 1 = s2d row
+  Y + ty - 1, sub-row sy, with 2 (ty - 1) + sy = sy' + ky - 1; same along x.  3/4 of the entries are structural zeros."""
+  O, I = w.shape[:2]
+  ws = torch.zeros((4 * O, 4 * I, 3, 3), dtype=w.dtype)
+  for sy_o in range(2):
+    for sx_o in range(2):
+      o0 = (sy_o * 2 + sx_o) * O
+      for ky in range(3):
+        for kx in range(3):
+          ry, rx = sy_o + ky - 1, sx_o + kx - 1
+          ty, sy, tx, sx = ry // 2 + 1, ry % 2, rx // 2 + 1, rx % 2
+          c0 = (sy * 2 + sx) * I
+          ws[o0:o0 + O, c0:c0 + I, ty, tx] = w[:, :, ky, kx]
+  return ws
+
+
+def s2d_weights_3x3_s2(w):
+  """3x3 stride-2 pad-1 conv [O, I, 3, 3] -> a 2x2 stride-1 conv [O, 4 I, 2, 2] over the space-to-depth input, padded on
+  the top / left only: input row 2 oy - 1 + ky = s2d row oy + ty - 1, sub-row sy with (ty, sy) = (0, 1), (1, 0), (1, 1)
+  for ky = 0, 1, 2; same along x."""
+  O, I = w.shape[:2]
+  ws = torch.zeros((O, 4 * I, 2, 2), dtype=w.dtype)
+  tap = ((0, 1), (1, 0), (1, 1))
+  for ky in range(3):
+    for kx in range(3):
+      (ty, sy), (tx, sx) = tap[ky], tap[kx]
+      c0 = (sy * 2 + sx) * I
+      ws[:, c0:c0 + I, ty, tx] = w[:, :, ky, kx]
+  return ws
+
+
 class DLA34Engine(object):
 
   def __init__(self, state_dict, heads, B, H, W, precision='bf16', device='cuda',
@@ -82,6 +115,8 @@ class DLA34Engine(object):
     self.keep = []         # device tensors referenced by raw pointers
     self.named = {}        # name -> TV (for per-stage parity tests)
     self.head_descs = {}   # head -> final ConvDesc (to toggle the fused activation)
+    self.algo_flops = {}   # op name -> flops of the reference layer, where the launch shape carries structural zeros
+    self.s2d_named = set() # named intermediates stored space-to-depth ([B, H/2, W/2, (sy, sx, 16)])
     self.n_sm = 148
     self.debug_sync = bool(int(__import__('os').environ.get('CTB_DEBUG_SYNC', '0')))
     self.use_halo = use_halo and precision == 'bf16'
@@ -195,8 +230,9 @@ class DLA34Engine(object):
       assert out.shape[:3] == (self.B, OH, OW) and out.dtype == torch.float32
       d.out, d.ld_out = out.data_ptr(), out.shape[-1]
     elif out_mode == L.CT_OUT_NHWC_S2D:
-      assert engine == L.CT_ENGINE_TCGEN05_HALO and (out.H, out.W, out.C, out.ld) == (OH // 2, OW // 2, 4 * C_out, 4 * C_out)
-      d.out, d.ld_out = out.ptr, C_out
+      co = 16 if sum3 else C_out
+      assert engine == L.CT_ENGINE_TCGEN05_HALO and (out.H, out.W, out.C, out.ld) == (OH // 2, OW // 2, 4 * co, 4 * co)
+      d.out, d.ld_out = out.ptr, co
       self.named[name] = out
     else:
       assert (out.H, out.W) == (OH, OW) and out.C == (16 if sum3 else C_out), (name, out.H, out.W, out.C, OH, OW, C_out)
@@ -301,7 +337,8 @@ class DLA34Engine(object):
       shst[si] = sh
     self.stem_w = self._dev(wst.to(f32).contiguous())
     self.stem_shift = self._dev(shst.to(f32).contiguous())
-    x0 = TV(self._buf(H, W, 16), 0, 16)
+    s2d = self.s2d_level1 and H % 2 == 0 and W % 2 == 0      # stem -> level0 -> level1 on the space-to-depth grid
+    x0 = TV(self._buf(H // 2, W // 2, 64), 0, 64) if s2d else TV(self._buf(H, W, 16), 0, 16)
     if self.use_halo:
       # tensor-core stem: pack (img, pre, hm) -> bf16 NHWC [.,8], one 7x7 conv 8 -> 48 (block-diagonal over the
       # three stems) whose epilogue applies ReLU per stem and sums them (dla.py:307-311)
@@ -310,7 +347,10 @@ class DLA34Engine(object):
       w48 = torch.zeros((48, 8, 7, 7), dtype=torch.float64)
       for si, (c0, cn) in enumerate(((0, 3), (3, 3), (6, 1))):
         w48[16 * si:16 * si + 16, c0:c0 + cn] = wst[:, c0:c0 + cn, :].reshape(7, 7, cn, 16).permute(3, 2, 0, 1)
-      self.stem_desc = self._conv('stem', x8, w48, shst.reshape(48), x0, 7, 1, relu=False, sum3=7)
+      self.stem_desc = self._conv('stem', x8, w48, shst.reshape(48), x0, 7, 1, relu=False, sum3=7,
+                                  out_mode=L.CT_OUT_NHWC_S2D if s2d else L.CT_OUT_NHWC)
+      if s2d:
+        self.s2d_named.add('stem')
     elif self.x3:
       # bf16x3 stem: pack (img, pre, hm) -> fp32 NHWC [.,8], one 7x7 conv 8 -> 48 (block-diagonal over the three stems)
       # with shift + ReLU per stem; the sum of the three (dla.py:307-311) is folded into level0, whose 3x3 conv reads
@@ -338,7 +378,7 @@ class DLA34Engine(object):
 
     # ---- level0 / level1 ----
     l1 = TV(self._buf(H // 2, W // 2, 32), 0, 32)
-    if not (self.s2d_level1 and H % 2 == 0 and W % 2 == 0):
+    if not s2d:
       l0 = TV(self._buf(H, W, 16), 0, 16)
       if self.x3:
         w0, sh0 = self._fold('base.level0.0', 'base.level0.1')
@@ -347,22 +387,23 @@ class DLA34Engine(object):
         self._conv_bn('base.level0', x0, 'base.level0.0', 'base.level0.1', l0, 3, 1)
       self._conv_bn('base.level1', l0, 'base.level1.0', 'base.level1.1', l1, 3, 2)
     else:
-      # level1 (3x3 stride 2, 16 -> 32) as a stride-1 2x2 convolution over the space-to-depth view of level0's output
-      # ([B, H/2, W/2, 4 x 16], written in that layout by level0's epilogue): 64-channel 128-byte rows for the TMA and 16
-      # MMAs per 128 output pixels on the halo engine instead of three latency-bound gather slices (301 -> ~100 us).
-      # Input row 2*oy - 1 + ky = s2d row oy + ty - 1, sub-row sy with (ty, sy) = (0, 1), (1, 0), (1, 1) for ky = 0, 1, 2.
-      l0 = l0s = TV(self._buf(H // 2, W // 2, 64), 0, 64)      # (level0 is below first_level: not an input of DLAUp)
+      # The 16-channel 512x512 layers on the space-to-depth grid [B, H/2, W/2, (sy, sx, 16)] (written in that layout by
+      # the stem's epilogue, CT_OUT_NHWC_S2D): 128-byte pixel rows for the TMA instead of 32-byte ones (level0 was bound
+      # by the TMA's row rate), N = 64 per MMA instead of 16 at the same MMA count, and level1's stride 2 disappears.
+      #  level0 (3x3 s1 16 -> 16): output sub-pixel sy' reads full-res row 2Y + sy' + ky - 1 = s2d row Y + ty - 1, sub-row
+      #    sy with 2 (ty - 1) + sy = sy' + ky - 1  ->  a 3x3 convolution 64 -> 64 whose weights are 3/4 structural zeros.
+      #  level1 (3x3 s2 16 -> 32): input row 2 oy - 1 + ky = s2d row oy + ty - 1, sub-row sy with (ty, sy) = (0, 1), (1, 0),
+      #    (1, 1) for ky = 0, 1, 2  ->  a 2x2 convolution 64 -> 32 padded on the top / left only.
       w0, sh0 = self._fold('base.level0.0', 'base.level0.1')
-      self._conv('base.level0', x0, w0, sh0, l0s, 3, 1, out_mode=L.CT_OUT_NHWC_S2D)
+      w0s = s2d_weights_3x3_s1(w0)
+      l0 = TV(self._buf(H // 2, W // 2, 64), 0, 64)          # (level0 is below first_level: not an input of DLAUp)
+      self._conv('base.level0', x0, w0s, sh0.repeat(4), l0, 3, 1)
+      self.s2d_named.add('base.level0')
+      self.algo_flops['base.level0'] = 2.0 * B * H * W * 16 * 9 * 16
       w1, sh1 = self._fold('base.level1.0', 'base.level1.1')
-      w1s = torch.zeros((w1.shape[0], 64, 2, 2), dtype=w1.dtype)
-      tap = ((0, 1), (1, 0), (1, 1))
-      for ky in range(3):
-        for kx in range(3):
-          (ty, sy), (tx, sx) = tap[ky], tap[kx]
-          c0 = (sy * 2 + sx) * 16
-          w1s[:, c0:c0 + 16, ty, tx] = w1[:, :, ky, kx]
-      self._conv('base.level1', l0s, w1s, sh1, l1, 2, 1, out_hw=(H // 2, W // 2))
+      w1s = s2d_weights_3x3_s2(w1)
+      self._conv('base.level1', l0, w1s, sh1, l1, 2, 1, out_hw=(H // 2, W // 2))
+      self.algo_flops['base.level1'] = 2.0 * B * (H // 2) * (W // 2) * 32 * 9 * 16
 
     # ---- level2: Tree(1, 32->64, s2, level_root=False) ----
     h2, w2 = H // 4, W // 4
@@ -569,7 +610,7 @@ class DLA34Engine(object):
   def stage(self, name):
     """NCHW fp32 copy of a named intermediate (parity tests)."""
     t = self.named[name].tensor()
-    if name == 'base.level0' and t.shape[-1] == 64:      # written space-to-depth (CT_OUT_NHWC_S2D, see _build)
+    if name in self.s2d_named:                            # stored space-to-depth (see _build)
       B, h, w, _ = t.shape
       return t.reshape(B, h, w, 2, 2, 16).permute(0, 5, 1, 3, 2, 4).reshape(B, 16, 2 * h, 2 * w).float().contiguous()
     return t.permute(0, 3, 1, 2).float().contiguous()

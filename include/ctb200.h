@@ -63,7 +63,7 @@ typedef enum {
   CT_OUT_NHWC_S2D = 3    /* CT_OUT_NHWC written space-to-depth: pixel (y, x) lands at pixel (y/2, x/2), channels
                             [((y&1)*2 + (x&1)) * ld_out, +C_out) of a [B, OH/2, OW/2, 4*ld_out] tensor -- the input
                             layout of a stride-2 3x3 consumer run as a stride-1 2x2 convolution over 4*C channels
-                            (DLA level0 -> level1).  Halo engine only; OH, OW even; no residual. */
+                            (DLA stem -> level0 -> level1).  Halo engine only; OH, OW even; no residual. */
 } ct_out_mode;
 
 typedef enum {           /* per-launch transform applied to the fp32 NCHW head outputs */

@@ -57,8 +57,9 @@ def run_conv(engine, dtype, x_nchw, w, bias, stride, relu=True, residual=None, a
     out = torch.zeros((B, OH, OW, 32), dtype=torch.float32, device=dev)
     d.out, d.ld_out = out.data_ptr(), 32
   elif out_mode == L.CT_OUT_NHWC_S2D:
-    out = torch.zeros((B, OH // 2, OW // 2, 4 * O), dtype=act, device=dev)
-    d.out, d.ld_out = out.data_ptr(), O
+    oc = 16 if sum3 else O
+    out = torch.zeros((B, OH // 2, OW // 2, 4 * oc), dtype=act, device=dev)
+    d.out, d.ld_out = out.data_ptr(), oc
   else:
     oc = 16 if sum3 else O
     out = torch.zeros((B, OH, OW, oc), dtype=act, device=dev)
@@ -68,7 +69,7 @@ def run_conv(engine, dtype, x_nchw, w, bias, stride, relu=True, residual=None, a
   if out_mode == L.CT_OUT_NCHW_F32:
     return out
   if out_mode == L.CT_OUT_NHWC_S2D:   # undo: [B, OH/2, OW/2, (sy, sx, c)] -> [B, c, OH, OW]
-    return out.reshape(B, OH // 2, OW // 2, 2, 2, O).permute(0, 5, 1, 3, 2, 4).reshape(B, O, OH, OW).float()
+    return out.reshape(B, OH // 2, OW // 2, 2, 2, oc).permute(0, 5, 1, 3, 2, 4).reshape(B, oc, OH, OW).float()
   return out.permute(0, 3, 1, 2).float()
 
 

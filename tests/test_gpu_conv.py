@@ -222,6 +222,15 @@ def test_halo_even_kernel_and_space_to_depth_output():
                  out_mode=L.CT_OUT_NHWC_S2D).cpu()
   assert torch.equal(plain, s2d)                      # same values, only the layout differs
 
+  # the stem's sum-of-three epilogue writing space-to-depth (what level0-on-the-s2d-grid reads)
+  x8 = torch.randn(B, 8, H, W, generator=g)
+  w48 = torch.randn(48, 8, 7, 7, generator=g) * 0.05
+  b48 = torch.randn(48, generator=g) * 0.1
+  st_plain = run_conv(L.CT_ENGINE_TCGEN05_HALO, L.CT_BF16, x8.cuda(), w48, b48, 1, False, n_tile=48, sum3=7).cpu()
+  st_s2d = run_conv(L.CT_ENGINE_TCGEN05_HALO, L.CT_BF16, x8.cuda(), w48, b48, 1, False, n_tile=48, sum3=7,
+                    out_mode=L.CT_OUT_NHWC_S2D).cpu()
+  assert st_plain.shape == (B, 16, H, W) and torch.equal(st_plain, st_s2d)
+
   # composition: 3x3 stride-2 16 -> 32 == 2x2 stride-1 over the space-to-depth view with the regrouped weights
   w1 = torch.randn(32, 16, 3, 3, generator=g) * 0.1
   b1 = torch.randn(32, generator=g) * 0.1
