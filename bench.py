@@ -60,7 +60,37 @@ class ClockSampler(threading.Thread):
     super().__init__(daemon=True)
     self.gpu, self.rows, self.stop_flag = gpu, [], False
 
+  def _nvml(self):
+    """NVML directly (a sample per ~5 ms: the timed region of a 30-step run is 0.2 s, one nvidia-smi call 0.1 s)."""
+    try:
+      import pynvml as nv
+      nv.nvmlInit()
+      try:
+        h = nv.nvmlDeviceGetHandleByUUID('GPU-' + str(torch.cuda.get_device_properties(self.gpu).uuid))
+      except Exception:
+        h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+      mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+      bits = (('hw_slowdown', nv.nvmlClocksEventReasonHwSlowdown), ('hw_thermal_slowdown', nv.nvmlClocksEventReasonHwThermalSlowdown),
+              ('sw_thermal_slowdown', nv.nvmlClocksEventReasonSwThermalSlowdown), ('sw_power_cap', nv.nvmlClocksEventReasonSwPowerCap))
+      nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+    except Exception:
+      return False
+    while not self.stop_flag:
+      try:
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        try:
+          r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+          r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        self.rows.append([str(self.gpu), str(sm), str(mx), '', ''] + ['Active' if r & b else 'Not Active' for _, b in bits])
+      except Exception:
+        pass
+      time.sleep(0.005)
+    return True
+
   def run(self):
+    if self._nvml():
+      return
     while not self.stop_flag:
       try:
         r = subprocess.run(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,

@@ -70,7 +70,7 @@ class TrackDesc(C.Structure):
 
 
 EXPORTS = ['ct_packed_weight_bytes', 'ct_pack_weights', 'ct_conv_forward', 'ct_stem_forward',
-           'ct_pack_stem_input', 'ct_pack_stem_input_f32', 'ct_maxpool2', 'ct_upsample_add', 'ct_decode_workspace_bytes', 'ct_decode',
+           'ct_pack_stem_input', 'ct_pack_stem_input_f32', 'ct_maxpool2', 'ct_maxpool2_s2d', 'ct_upsample_add', 'ct_decode_workspace_bytes', 'ct_decode',
            'ct_render_pre_hm', 'ct_track_smem_bytes', 'ct_track_step', 'ct_render_tracks', 'ct_flip_merge',
            'ct_warp_affine_normalize', 'ct_last_error', 'ct_abi_version', 'ct_launch_count',
            'ct_reset_launch_count', 'ct_debug_trace', 'ct_debug_watch']
@@ -118,6 +118,7 @@ def lib():
   L.ct_pack_stem_input.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p]
   L.ct_pack_stem_input_f32.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p]
   L.ct_maxpool2.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p]
+  L.ct_maxpool2_s2d.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p]
   L.ct_upsample_add.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 9 + [C.c_void_p]
   L.ct_decode_workspace_bytes.restype = C.c_int64
   L.ct_decode_workspace_bytes.argtypes = [C.c_int32] * 4

@@ -474,6 +474,41 @@ extern "C" int ct_maxpool2(const void* x, void* out, int32_t dtype, int32_t B, i
   return after_launch();
 }
 
+// MaxPool2d(2,2) of a tensor stored space-to-depth ([B, H2, W2, (sy, sx, C)], CT_OUT_NHWC_S2D): the window of output pixel
+// p is the four C-channel groups of input pixel p -- a per-pixel max over channel groups, one 16-byte vector per thread.
+template <typename T>
+__global__ void maxpool2_s2d_kernel(const T* __restrict__ x, T* __restrict__ out, size_t P, int C, int ld_in, int ld_out) {
+  constexpr int V = VecIO<T>::N;
+  const int CV = C / V;
+  const size_t total = P * CV;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % CV) * V;
+    const size_t p = i / CV;
+    const T* s = x + p * ld_in + c;
+    float v0[V], v1[V], v2[V], v3[V];
+    VecIO<T>::ld(s, v0); VecIO<T>::ld(s + C, v1); VecIO<T>::ld(s + 2 * C, v2); VecIO<T>::ld(s + 3 * C, v3);
+#pragma unroll
+    for (int q = 0; q < V; ++q) v0[q] = fmaxf(fmaxf(v0[q], v1[q]), fmaxf(v2[q], v3[q]));
+    VecIO<T>::st(out + p * ld_out + c, v0);
+  }
+}
+
+extern "C" int ct_maxpool2_s2d(const void* x, void* out, int32_t dtype, int32_t B, int32_t H2, int32_t W2, int32_t C,
+                               int32_t ld_in, int32_t ld_out, void* stream) {
+  CT_REQUIRE(x && out, "null pointer");
+  const int vecw = dtype == CT_F32 ? 4 : 8;
+  CT_REQUIRE(C % vecw == 0 && ld_in % vecw == 0 && ld_out % vecw == 0 && ld_in >= 4 * C,
+             "channels / strides must be multiples of 16 bytes, ld_in >= 4 C");
+  const size_t P = (size_t)B * H2 * W2, total = P * (C / vecw);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == CT_F32)
+    maxpool2_s2d_kernel<float><<<ew_blocks(total), 256, 0, st>>>((const float*)x, (float*)out, P, C, ld_in, ld_out);
+  else
+    maxpool2_s2d_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, P, C,
+                                                                        ld_in, ld_out);
+  return after_launch();
+}
+
 extern "C" int ct_upsample_add(const void* x, const void* skip, const float* w, void* out, int32_t dtype,
                                int32_t B, int32_t H, int32_t W, int32_t C, int32_t f, int32_t ld_in,
                                int32_t ld_skip, int32_t ld_out, void* stream) {

@@ -248,11 +248,20 @@ class DLA34Engine(object):
   def _maxpool(self, x, out):
     self.ops.append(('pool', (x, out), 'maxpool'))
 
-  def _basic_block(self, p, x, out, stride, residual):
-    """BasicBlock dla.py:38-66: conv1-bn1-relu-conv2-bn2-(+residual)-relu."""
-    oh, ow = x.H // stride, x.W // stride
-    mid = TV(self._buf(oh, ow, out.C), 0, out.C)
-    self._conv_bn(p + '.conv1', x, p + '.conv1', p + '.bn1', mid, 3, stride, True)
+  def _basic_block(self, p, x, out, stride, residual, x_s2d=False):
+    """BasicBlock dla.py:38-66: conv1-bn1-relu-conv2-bn2-(+residual)-relu.  x_s2d: x is stored space-to-depth
+    ([B, H/2, W/2, 4 C]) and stride is 2: conv1 runs as a 2x2 stride-1 convolution over it (s2d_weights_3x3_s2)."""
+    if x_s2d:
+      assert stride == 2
+      oh, ow = x.H, x.W
+      mid = TV(self._buf(oh, ow, out.C), 0, out.C)
+      w, sh = self._fold(p + '.conv1', p + '.bn1')
+      self._conv(p + '.conv1', x, s2d_weights_3x3_s2(w), sh, mid, 2, 1, out_hw=(oh, ow))
+      self.algo_flops[p + '.conv1'] = 2.0 * self.B * oh * ow * w.shape[0] * 9 * w.shape[1]
+    else:
+      oh, ow = x.H // stride, x.W // stride
+      mid = TV(self._buf(oh, ow, out.C), 0, out.C)
+      self._conv_bn(p + '.conv1', x, p + '.conv1', p + '.bn1', mid, 3, stride, True)
     self._conv_bn(p, mid, p + '.conv2', p + '.bn2', out, 3, 1, True, residual)
 
   def _deform(self, p, x, out):
@@ -377,8 +386,8 @@ class DLA34Engine(object):
     self.named['stem'] = x0
 
     # ---- level0 / level1 ----
-    l1 = TV(self._buf(H // 2, W // 2, 32), 0, 32)
     if not s2d:
+      l1 = TV(self._buf(H // 2, W // 2, 32), 0, 32)
       l0 = TV(self._buf(H, W, 16), 0, 16)
       if self.x3:
         w0, sh0 = self._fold('base.level0.0', 'base.level0.1')
@@ -402,20 +411,27 @@ class DLA34Engine(object):
       self.algo_flops['base.level0'] = 2.0 * B * H * W * 16 * 9 * 16
       w1, sh1 = self._fold('base.level1.0', 'base.level1.1')
       w1s = s2d_weights_3x3_s2(w1)
-      self._conv('base.level1', l0, w1s, sh1, l1, 2, 1, out_hw=(H // 2, W // 2))
+      # level1's own output goes out space-to-depth as well ([B, H/4, W/4, (sy, sx, 32)]): level2 reads it through a 2x2
+      # max-pool (= a max over the four channel groups) and a 3x3 stride-2 conv (= a 2x2 conv over 128 channels)
+      l1 = TV(self._buf(H // 4, W // 4, 128), 0, 128)
+      self._conv('base.level1', l0, w1s, sh1, l1, 2, 1, out_hw=(H // 2, W // 2), out_mode=L.CT_OUT_NHWC_S2D)
+      self.s2d_named.add('base.level1')
       self.algo_flops['base.level1'] = 2.0 * B * (H // 2) * (W // 2) * 32 * 9 * 16
 
     # ---- level2: Tree(1, 32->64, s2, level_root=False) ----
     h2, w2 = H // 4, W // 4
     cat2 = self._buf(h2, w2, 128)
     bottom2 = TV(self._buf(h2, w2, 32), 0, 32)
-    self._maxpool(l1, bottom2)
+    if s2d:
+      self.ops.append(('pool_s2d', (l1, bottom2), 'maxpool'))
+    else:
+      self._maxpool(l1, bottom2)
     res2 = TV(self._buf(h2, w2, 64), 0, 64)
     self._conv_bn('base.level2.project', bottom2, 'base.level2.project.0', 'base.level2.project.1',
                   res2, 1, 1, relu=False)
     x1 = TV(cat2, 64, 64)
     x2 = TV(cat2, 0, 64)
-    self._basic_block('base.level2.tree1', l1, x1, 2, res2)
+    self._basic_block('base.level2.tree1', l1, x1, 2, res2, x_s2d=s2d)
     self._basic_block('base.level2.tree2', x1, x2, 1, x1)
     l2 = TV(self._buf(h2, w2, 64), 0, 64)
     self._conv_bn('base.level2', TV(cat2, 0, 128), 'base.level2.root.conv', 'base.level2.root.bn', l2, 1)
@@ -548,6 +564,9 @@ class DLA34Engine(object):
       rc = lib.ct_pack_stem_input(img_ptr, pre_ptr, hm_ptr, C.c_void_p(pl.ptr), self.B, self.H, self.W, st)
     elif kind == 'pack32':
       rc = lib.ct_pack_stem_input_f32(img_ptr, pre_ptr, hm_ptr, C.c_void_p(pl.ptr), self.B, self.H, self.W, st)
+    elif kind == 'pool_s2d':
+      x, o = pl
+      rc = lib.ct_maxpool2_s2d(C.c_void_p(x.ptr), C.c_void_p(o.ptr), self.ct_dtype, self.B, x.H, x.W, o.C, x.ld, o.ld, st)
     elif kind == 'pool':
       x, o = pl
       rc = lib.ct_maxpool2(C.c_void_p(x.ptr), C.c_void_p(o.ptr), self.ct_dtype, self.B, x.H, x.W, x.C,
@@ -612,5 +631,6 @@ class DLA34Engine(object):
     t = self.named[name].tensor()
     if name in self.s2d_named:                            # stored space-to-depth (see _build)
       B, h, w, _ = t.shape
-      return t.reshape(B, h, w, 2, 2, 16).permute(0, 5, 1, 3, 2, 4).reshape(B, 16, 2 * h, 2 * w).float().contiguous()
+      c = t.shape[-1] // 4
+      return t.reshape(B, h, w, 2, 2, c).permute(0, 5, 1, 3, 2, 4).reshape(B, c, 2 * h, 2 * w).float().contiguous()
     return t.permute(0, 3, 1, 2).float().contiguous()

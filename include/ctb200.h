@@ -150,6 +150,11 @@ int ct_pack_stem_input_f32(const float* img, const float* pre_img, const float* 
 int ct_maxpool2(const void* x, void* out, int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t C,
                 int32_t ld_in, int32_t ld_out, void* stream);
 
+/* the same pooling of a tensor stored space-to-depth (CT_OUT_NHWC_S2D): x [B,H2,W2,(sy,sx,C)] -> out [B,H2,W2,C],
+ * out[p][c] = max over the four C-channel groups of pixel p */
+int ct_maxpool2_s2d(const void* x, void* out, int32_t dtype, int32_t B, int32_t H2, int32_t W2, int32_t C,
+                    int32_t ld_in, int32_t ld_out, void* stream);
+
 /* out[b,oy,ox,c] = skip[...] + sum_{ky,kx} x[b,(oy+pad-ky)/f,(ox+pad-kx)/f,c] * w[ky,kx,c]
  * (depthwise ConvTranspose2d, kernel 2f, stride f, pad f/2; w fp32 channel-last [2f][2f][C]). */
 int ct_upsample_add(const void* x, const void* skip, const float* w, void* out, int32_t dtype,

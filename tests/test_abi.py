@@ -15,7 +15,7 @@ def _declared():
 
 def test_header_declares_entry_points():
   names = _declared()
-  for must in ('ct_conv_forward', 'ct_decode', 'ct_stem_forward', 'ct_maxpool2', 'ct_upsample_add',
+  for must in ('ct_conv_forward', 'ct_decode', 'ct_stem_forward', 'ct_maxpool2', 'ct_maxpool2_s2d', 'ct_upsample_add',
                'ct_pack_weights', 'ct_last_error'):
     assert must in names
 

@@ -231,6 +231,21 @@ def test_halo_even_kernel_and_space_to_depth_output():
                     out_mode=L.CT_OUT_NHWC_S2D).cpu()
   assert st_plain.shape == (B, 16, H, W) and torch.equal(st_plain, st_s2d)
 
+  # level2's inputs: 2x2 max-pool of a space-to-depth tensor, and the 3x3 stride-2 32 -> 64 conv as a 2x2 over 128 channels
+  import ctypes as C
+  y = torch.randn(B, 32, H, W, generator=g).bfloat16()
+  ys = y.reshape(B, 32, H // 2, 2, W // 2, 2).permute(0, 2, 4, 3, 5, 1).reshape(B, H // 2, W // 2, 128).contiguous().cuda()
+  po = torch.empty(B, H // 2, W // 2, 32, dtype=torch.bfloat16, device='cuda')
+  L.check(L.lib().ct_maxpool2_s2d(L.ptr(ys), L.ptr(po), L.CT_BF16, B, H // 2, W // 2, 32, 128, 32, L.stream_ptr()))
+  assert torch.equal(po.permute(0, 3, 1, 2).float().cpu(), F.max_pool2d(y.float(), 2, 2))
+  from centertrack_b200.engine import s2d_weights_3x3_s2
+  w2 = torch.randn(64, 32, 3, 3, generator=g) * 0.08
+  b2 = torch.randn(64, generator=g) * 0.1
+  via2 = run_conv(L.CT_ENGINE_TCGEN05_HALO, L.CT_BF16, ys.permute(0, 3, 1, 2).float(), s2d_weights_3x3_s2(w2), b2, 1, True,
+                  n_tile=64).cpu()
+  ref2 = F.relu(F.conv2d(y.float(), w2.bfloat16().float(), b2, 2, 1))
+  assert (via2 - ref2).abs().max() < 2e-2 * max(1.0, float(ref2.abs().max()))
+
   # composition: 3x3 stride-2 16 -> 32 == 2x2 stride-1 over the space-to-depth view with the regrouped weights
   w1 = torch.randn(32, 16, 3, 3, generator=g) * 0.1
   b1 = torch.randn(32, generator=g) * 0.1
