@@ -220,7 +220,9 @@ def _op_group(kind, pl, L):
   if kind != 'conv':
     return kind
   if pl.a_mode in (L.CT_A_DCN, L.CT_A_DCN_WIN):
-    return 'dcn_main'
+    # window DCN with one N tile of <= 128 channels runs the persistent kernel (conv_tc.cu conv_forward_tc, CTB_DCN_PERSIST)
+    persist = pl.a_mode == L.CT_A_DCN_WIN and pl.C_out <= 128 and os.environ.get('CTB_DCN_PERSIST', '1') != '0'
+    return 'dcn_persist' if persist else 'dcn_tc'
   return {L.CT_ENGINE_TCGEN05: 'conv_tc', L.CT_ENGINE_TCGEN05_HALO: 'conv_halo', L.CT_ENGINE_SIMT: 'conv_simt',
           L.CT_ENGINE_TCGEN05_X3: 'conv_tc'}[pl.engine]
 
@@ -478,40 +480,35 @@ def main():
   if os.path.exists(tp):
     traffic_per_frame = json.load(open(tp)).get(cfg if args.precision == 'bf16' else '', {})
 
-  def tensor_roof(gname, label):
-    gr = groups.get(gname)
-    if not gr or gr['ms'] <= 0:
+  def merged(keys):
+    ms = sum(groups.get(k, {'ms': 0.0})['ms'] for k in keys)
+    fl = sum(groups.get(k, {'flop': 0.0})['flop'] for k in keys)
+    n = sum(groups.get(k, {'launches': 0})['launches'] for k in keys)
+    tr = [traffic_per_frame.get({'conv_tc': 'conv_tc_plain'}.get(k, k)) for k in keys if groups.get(k)]
+    if ms <= 0:
       return None
-    ach = gr['flop'] / (gr['ms'] / 1000.0) / 1e12
-    tr = traffic_per_frame.get(gname)
-    return {'kernel': label % gr['launches'], 'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s',
-            'frac': ach / peak_tf if peak_tf else None, 'traffic': tr * B if tr is not None else None,
-            'ms_per_step': round(gr['ms'], 4), 'share_of_step': gr['ms'] / sum_ms, 'gflop_per_step': gr['flop'] / 1e9}
+    ach = fl / (ms / 1000.0) / 1e12
+    return {'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf if peak_tf else None,
+            'traffic': (sum(tr) * B) if tr and all(t is not None for t in tr) else None, 'ms_per_step': round(ms, 4),
+            'share_of_step': ms / sum_ms, 'gflop_per_step': fl / 1e9, 'launches': n}
 
-  dcn = tensor_roof('dcn_main', 'conv_tc_kernel, CT_A_DCN (%d DCNv2 launches of one step)')
-  tc = tensor_roof('conv_tc', 'conv_tc_kernel, plain gather (%d stride-2 / deep-layer launches)')
-  halo = tensor_roof('conv_halo', 'conv_halo_kernel (%d launches)')
-  simt = tensor_roof('conv_simt', 'conv_simt_kernel (%d launches)')
-  # dominant kernel = conv_tc_kernel (plain + DCN launches), as in round 1, with its two populations split out below
-  both_ms = sum(groups.get(k, {'ms': 0})['ms'] for k in ('dcn_main', 'conv_tc'))
-  both_fl = sum(groups.get(k, {'flop': 0})['flop'] for k in ('dcn_main', 'conv_tc'))
+  # one entry per kernel FUNCTION; the headline is the function with the largest share of the step
+  fn = {'conv_halo_kernel': merged(['conv_halo']), 'dcn_persist_kernel': merged(['dcn_persist']),
+        'conv_tc_kernel': merged(['dcn_tc', 'conv_tc']), 'conv_simt_kernel': merged(['conv_simt'])}
+  fn = {k: v for k, v in fn.items() if v}
+  dcn = merged(['dcn_persist', 'dcn_tc'])                   # all 16 DCNv2 main launches, whichever kernel ran them
+  tc = merged(['conv_tc'])                                  # plain gather launches of conv_tc_kernel
+  halo = fn.get('conv_halo_kernel')
+  simt = fn.get('conv_simt_kernel')
   hm_bytes = float(eng.outputs['hm'].numel() * 4 + (eng.outputs['hm_hp'].numel() * 4 if 'hm_hp' in eng.outputs else 0))
   dec_gbs = hm_bytes / (decode_ms * 1e-3) / 1e9 if decode_ms > 0 else 0.0
-  if both_ms > 0:
-    ach = both_fl / (both_ms / 1000.0) / 1e12
-    t_all = [traffic_per_frame.get(k) for k in ('dcn_main', 'conv_tc')]
-    roofline = {'kernel': 'conv_tc_kernel (all %d gather-engine tcgen05 conv/DCN launches of one step)' %
-                sum(groups.get(k, {'launches': 0})['launches'] for k in ('dcn_main', 'conv_tc')),
-                'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                'frac': ach / peak_tf if peak_tf else None,
-                'traffic': (sum(t_all) * B) if all(t is not None for t in t_all) else None,
-                'share_of_step': both_ms / sum_ms}
-  else:                                                       # fp32 SIMT engine
-    roofline = dict(simt or {})
+  top = max(fn, key=lambda k: fn[k]['ms_per_step'])
+  roofline = dict(fn[top])
+  roofline['kernel'] = '%s (%d launches of one step)' % (top, roofline.pop('launches'))
   roofline.update({
       'traffic_unit': 'bytes per step (all launches of the kernel), ncu capture at 32 frames/step scaled',
       'peak_source': peak_src, 'method': method,
-      'kernels': {'dcn_main': dcn, 'conv_tc_plain': tc, 'conv_halo': halo, 'conv_simt': simt},
+      'kernels': dict(fn, dcn_main=dcn, conv_tc_plain=tc),
       'ms_by_group': {k: round(v['ms'], 4) for k, v in groups.items()},
       'top_ops_us': [[n, round(t * 1000, 1)] for t, n in sorted(((dt, name) for (kind, pl, name), dt in zip(eng.ops, op_ms)),
                                                              reverse=True)[:24]],

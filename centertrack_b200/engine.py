@@ -108,6 +108,7 @@ class DLA34Engine(object):
     # the persistent window kernel (CTB_DCN_PERSIST, default on) also wins on 128 -> 128 at 64x64 (100 vs 124 us)
     self.dcn_window_all = bool(int(__import__('os').environ.get('CTB_DCN_PERSIST', '1')))
     self.ntile_cap = int(__import__('os').environ.get('CTB_NTILE_CAP', '256'))
+    self.gather_128 = bool(int(__import__('os').environ.get('CTB_GATHER_128', '0')))   # experiment: level3's 3x3 on the gather engine
     self.depth_scale = float(depth_scale)
     self.has_pre_img = has_pre_img and ('base.pre_img_layer.0.weight' in self.sd)
     self.has_pre_hm = has_pre_hm and ('base.pre_hm_layer.0.weight' in self.sd)
@@ -195,7 +196,8 @@ class DLA34Engine(object):
     if engine == L.CT_ENGINE_TCGEN05_X3 and n_tile > 128 and a_mode == L.CT_A_DCN:
       n_tile = 128            # x3 DCN: two 36 KB-table stages of (32 + 2 x n_tile/8) KB must fit
     if engine == L.CT_ENGINE_TCGEN05 and self.use_halo and a_mode == L.CT_A_CONV and stride == 1 and kh == kw and \
-        (C_in in (16, 32, 48, 64, 128, 192, 256) or (C_in == 8 and sum3)):
+        (C_in in (16, 32, 48, 64, 128, 192, 256) or (C_in == 8 and sum3)) and \
+        not (self.gather_128 and C_in == 128 and C_out == 128 and kh == 3):
       k = kh
       # stride-1 layer whose weights fit in smem: TMA halo tile + descriptor-shifted taps (csrc/conv_halo.cu)
       nblk = k * ((k + 1) // 2) if C_in == 8 else k * k * (C_in // 16)

@@ -52,7 +52,7 @@ conv_ops = [o for o in ops if o[0] == 'conv']
 ci = 0
 for o in out:
   o['op'] = ''
-  if 'conv_tc_kernel' in o['kernel'] or 'conv_halo_kernel' in o['kernel'] or 'conv_simt_kernel' in o['kernel']:
+  if any(k in o['kernel'] for k in ('conv_tc_kernel', 'dcn_persist_kernel', 'conv_halo_kernel', 'conv_simt_kernel')):
     if ci < len(conv_ops):
       o['op'] = conv_ops[ci][1]
       o['a_mode'] = conv_ops[ci][3] if len(conv_ops[ci]) > 3 else ''
@@ -60,7 +60,10 @@ for o in out:
 groups = {}
 for o in out:
   k = o['kernel']
-  g = 'dcn_main' if ('conv_tc' in k and o.get('a_mode') in ('1', '2')) else 'conv_tc' if 'conv_tc' in k else \
+  # kernel FUNCTIONS: dcn_persist_kernel (window DCN, C_out <= 128), conv_tc_kernel split into its DCN launches
+  # (C_out = 256 / non-window) and its plain gather launches, conv_halo_kernel
+  g = 'dcn_persist' if 'dcn_persist' in k else 'dcn_tc' if ('conv_tc' in k and o.get('a_mode') in ('1', '2')) else \
+      'conv_tc_plain' if 'conv_tc' in k else \
       'conv_halo' if 'conv_halo' in k else 'decode' if 'decode' in k else 'track' if 'track_step' in k else \
       'upsample' if 'upsample' in k else 'other'
   o['group'] = g
@@ -80,5 +83,6 @@ for i, o in enumerate(out):
 tj = os.path.join(os.path.dirname(os.path.abspath(raw)), 'traffic.json')
 cur = json.load(open(tj)) if os.path.exists(tj) else {}
 cfg = os.environ.get('CT_CFG', 'coco_tracking')
-cur[cfg] = {k: (g['rd'] + g['wr']) / frames for k, g in groups.items() if k in ('dcn_main', 'conv_tc', 'conv_halo', 'decode')}
+cur[cfg] = {k: (g['rd'] + g['wr']) / frames for k, g in groups.items()
+            if k in ('dcn_persist', 'dcn_tc', 'conv_tc_plain', 'conv_halo', 'decode', 'upsample')}
 json.dump(cur, open(tj, 'w'), indent=1, sort_keys=True)
