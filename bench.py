@@ -59,22 +59,28 @@ class ClockSampler(threading.Thread):
   def __init__(self, gpu):
     super().__init__(daemon=True)
     self.gpu, self.rows, self.stop_flag = gpu, [], False
-
-  def _nvml(self):
-    """NVML directly (a sample per ~5 ms: the timed region of a 30-step run is 0.2 s, one nvidia-smi call 0.1 s)."""
+    # NVML is set up HERE, before the timed region (import + nvmlInit take longer than a 0.2 s timed region on a cold
+    # box); the thread then takes a sample every ~5 ms.  nvidia-smi (0.1 s per call) is the fall-back.
+    self.nv = self.h = None
     try:
       import pynvml as nv
       nv.nvmlInit()
       try:
-        h = nv.nvmlDeviceGetHandleByUUID('GPU-' + str(torch.cuda.get_device_properties(self.gpu).uuid))
+        h = nv.nvmlDeviceGetHandleByUUID('GPU-' + str(torch.cuda.get_device_properties(gpu).uuid))
       except Exception:
-        h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
-      mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-      bits = (('hw_slowdown', nv.nvmlClocksEventReasonHwSlowdown), ('hw_thermal_slowdown', nv.nvmlClocksEventReasonHwThermalSlowdown),
-              ('sw_thermal_slowdown', nv.nvmlClocksEventReasonSwThermalSlowdown), ('sw_power_cap', nv.nvmlClocksEventReasonSwPowerCap))
+        h = nv.nvmlDeviceGetHandleByIndex(gpu)
+      self.mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+      self.bits = (('hw_slowdown', nv.nvmlClocksEventReasonHwSlowdown), ('hw_thermal_slowdown', nv.nvmlClocksEventReasonHwThermalSlowdown),
+                   ('sw_thermal_slowdown', nv.nvmlClocksEventReasonSwThermalSlowdown), ('sw_power_cap', nv.nvmlClocksEventReasonSwPowerCap))
       nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+      self.nv, self.h = nv, h
     except Exception:
+      self.nv = self.h = None
+
+  def _nvml(self):
+    if self.nv is None:
       return False
+    nv, h = self.nv, self.h
     while not self.stop_flag:
       try:
         sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
@@ -82,7 +88,7 @@ class ClockSampler(threading.Thread):
           r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
         except Exception:
           r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-        self.rows.append([str(self.gpu), str(sm), str(mx), '', ''] + ['Active' if r & b else 'Not Active' for _, b in bits])
+        self.rows.append([str(self.gpu), str(sm), str(self.mx), '', ''] + ['Active' if r & b else 'Not Active' for _, b in self.bits])
       except Exception:
         pass
       time.sleep(0.005)
@@ -404,10 +410,10 @@ def main():
     if gathered is not None:               # the one collective of the path: fixed-size result gather
       dist.all_gather_into_tensor(gathered, gather_src)
 
+  sampler = ClockSampler(local) if rank == 0 else None      # NVML set up before the warm-up, sampling starts after it
   for _ in range(args.warmup):
     dev_step()
   barrier()
-  sampler = ClockSampler(local)
   if rank == 0:
     sampler.start()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
