@@ -12,18 +12,47 @@
 // memory and selects its top-K there; the last CTA of a batch element to finish merges the C*K candidates by
 // (value, class, index) and writes the K records.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace ctb {
 
 constexpr int DT = 512;          // threads per CTA (3 CTAs per SM: 40 registers, 37 KB of shared memory each)
 constexpr int MAXK = 512;
-constexpr int PEAK_CAP = 4096;   // compact list of kept positive peaks (indices), 16 KB
+constexpr int PEAK_CAP = 4096;   // compact list of kept positive peaks (64-bit keys), 32 KB
+constexpr int PLANE_CAP = 65536; // bytes of one class plane staged in shared memory by bulk copies (128 x 128 fp32)
+constexpr int DEC_NCH = 4;       // ... in this many row chunks, one mbarrier each
+
+// bulk-copy plumbing of the staged plane (the plane of a (b, class) is contiguous in the reference's NCHW layout)
+__device__ __forceinline__ uint32_t dec_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dec_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void dec_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void dec_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void dec_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (!done) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (++spins > 20000000u) __trap();     // a protocol bug must not hang the GPU
+  }
+}
 
 struct DecodeArgs {
   ct_decode_desc d;
   int* counters;
   unsigned long long* cand;      // [B][C+J][K]
   int kpad;                      // pow2 >= K
+  int bulk;                      // 1: planes are staged in shared memory by cp.async.bulk (dynamic smem = PLANE_CAP + list)
+  int key_cap;                   // 64-bit keys the dynamic shared memory can hold (phase-2 merge keys staged there)
+  int dbg;                       // CTB_DEC_DEBUG (tools/decode_time.py): 1 = stop after the streaming NMS, 2 = skip the
+                                 // per-image merge -- timing experiments only, results are then incomplete
 };
 
 struct SelState {
@@ -131,7 +160,10 @@ __device__ __forceinline__ bool nms_keep(const float* sp, int i, int H, int W) {
   return m == c;
 }
 
-__global__ void __launch_bounds__(DT, 3)
+// BULK: planes staged in shared memory by bulk copies (PLANE_CAP + list = 96 KB: two CTAs per SM, 64 registers);
+// otherwise streamed through registers (32 KB: three CTAs per SM, 40 registers).
+template <bool BULK>
+__global__ void __launch_bounds__(DT, BULK ? 2 : 3)
 decode_kernel(DecodeArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int hist[256];
@@ -140,6 +172,7 @@ decode_kernel(DecodeArgs a) {
   __shared__ int sel_n;
   __shared__ int peak_n;
   __shared__ int is_last;
+  __shared__ __align__(8) unsigned long long pbar[DEC_NCH];
 
   const ct_decode_desc& d = a.d;
   const int tid = threadIdx.x;
@@ -155,17 +188,42 @@ decode_kernel(DecodeArgs a) {
   {
     const float* src = pl < d.C ? d.hm + ((size_t)b * d.C + pl) * HW
                                 : d.hm_hp + ((size_t)b * d.J + (pl - d.C)) * HW;
-    unsigned long long* klist = reinterpret_cast<unsigned long long*>(smem_raw);
-    if (tid == 0) { peak_n = 0; sel_n = 0; }
+    // a.bulk: the plane is fetched by DEC_NCH cp.async.bulk copies into shared memory (one thread, no registers, the whole
+    // 64 KB in flight at once: the register-streamed form keeps one 512-byte row per warp in flight and measured
+    // 1.7 TB/s for the NMS alone) and the same rolling NMS reads its rows from there as the chunks land.
+    float* plane = reinterpret_cast<float*>(smem_raw);
+    unsigned long long* klist = reinterpret_cast<unsigned long long*>(smem_raw + (BULK ? PLANE_CAP : 0));
+    const bool vec_ok = (W & 3) == 0 && (reinterpret_cast<size_t>(src) & 15) == 0;
+    const bool bulk = BULK && vec_ok;
+    const int chunk_rows = (H + DEC_NCH - 1) / DEC_NCH;
+    if (tid == 0) {
+      peak_n = 0; sel_n = 0;
+      if (bulk) {
+        for (int c = 0; c < DEC_NCH; ++c) dec_mbar_init(dec_smem_u32(&pbar[c]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int c = 0; c < DEC_NCH; ++c) {
+          const int r0 = c * chunk_rows;
+          if (r0 >= H) break;
+          const uint32_t bytes = (uint32_t)((H - r0 < chunk_rows ? H - r0 : chunk_rows) * W) * 4u;
+          dec_mbar_expect_tx(dec_smem_u32(&pbar[c]), bytes);
+          dec_bulk_g2s(dec_smem_u32(plane + (size_t)r0 * W), src + (size_t)r0 * W, bytes, dec_smem_u32(&pbar[c]));
+        }
+      }
+    }
     for (int i = tid; i < a.kpad; i += DT) sel[i] = 0ull;
     __syncthreads();
-    const bool vec_ok = (W & 3) == 0 && (reinterpret_cast<size_t>(src) & 15) == 0;
     if (vec_ok) {
       const int lane = tid & 31, warp = tid >> 5;
       constexpr int NW = DT / 32;
       const int rpw = (H + NW - 1) / NW;
       const int y0 = warp * rpw;
       const float NEG = __int_as_float(0xff800000);
+      if (bulk) {                                       // rows y0-1 .. y0+rpw of this warp: wait for the chunks holding them
+        const int y_hi = (y0 + rpw < H ? y0 + rpw : H - 1);
+        if (y0 < H)
+          for (int c = 0; c <= y_hi / chunk_rows; ++c) dec_mbar_wait(dec_smem_u32(&pbar[c]), 0u);
+      }
+      const float* rows = bulk ? plane : src;           // generic pointer: shared or global
       for (int x0 = 0; x0 < W; x0 += 128) {
         const int x = x0 + 4 * lane;
         const bool xin = x < W;
@@ -174,10 +232,11 @@ decode_kernel(DecodeArgs a) {
         auto load_row = [&](int y, float4& v, float4& h) {
           const bool yin = y >= 0 && y < H;                                    // warp-uniform
           v = make_float4(NEG, NEG, NEG, NEG);
-          if (yin && xin) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)y * W + x));
+          if (yin && xin) v = bulk ? *reinterpret_cast<const float4*>(rows + (size_t)y * W + x)
+                                   : __ldg(reinterpret_cast<const float4*>(src + (size_t)y * W + x));
           float l = __shfl_up_sync(0xffffffffu, v.w, 1), r = __shfl_down_sync(0xffffffffu, v.x, 1);
-          if (lane == 0) l = (yin && x0 > 0) ? __ldg(src + (size_t)y * W + x0 - 1) : NEG;
-          if (lane == 31) r = (yin && x + 4 < W) ? __ldg(src + (size_t)y * W + x + 4) : NEG;
+          if (lane == 0) l = (yin && x0 > 0) ? rows[(size_t)y * W + x0 - 1] : NEG;
+          if (lane == 31) r = (yin && x + 4 < W) ? rows[(size_t)y * W + x + 4] : NEG;
           h.x = fmaxf(fmaxf(l, v.x), v.y); h.y = fmaxf(fmaxf(v.x, v.y), v.z);
           h.z = fmaxf(fmaxf(v.y, v.z), v.w); h.w = fmaxf(fmaxf(v.z, v.w), r);
         };
@@ -194,14 +253,14 @@ decode_kernel(DecodeArgs a) {
             unsigned bits = 0;
 #pragma unroll
             for (int c = 0; c < 4; ++c) bits |= (xin && vc[c] > 0.f && mx[c] == vc[c]) ? (1u << c) : 0u;
+            // inclusive prefix of the per-lane peak counts (0..4) from three independent ballots of the count's bit planes
+            // (a 5-step shuffle scan is a 5-deep dependent chain per row); rows without a peak skip everything
             const int cnt = __popc(bits);
-            int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-              const int t = __shfl_up_sync(0xffffffffu, incl, o);
-              if (lane >= o) incl += t;
-            }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            const unsigned b0 = __ballot_sync(0xffffffffu, cnt & 1), b1 = __ballot_sync(0xffffffffu, cnt & 2),
+                           b2 = __ballot_sync(0xffffffffu, cnt & 4);
+            const unsigned le = 0xffffffffu >> (31 - lane);
+            const int incl = __popc(b0 & le) + 2 * __popc(b1 & le) + 4 * __popc(b2 & le);
+            const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
             if (total) {
               int base = 0;
               if (lane == 0) base = atomicAdd(&peak_n, total);
@@ -222,6 +281,7 @@ decode_kernel(DecodeArgs a) {
       }
     }
     __syncthreads();
+    if (a.dbg & 1) return;
     const int npk = peak_n;
     // The list is exact whenever it holds at least K peaks and did not overflow (zeros, which the index-ordered tie
     // rule would otherwise have to rank, are then out of the race).  Degenerate planes (fewer than K positive peaks,
@@ -283,7 +343,7 @@ decode_kernel(DecodeArgs a) {
     if (is_last) a.counters[b] = 0;
   }
   __syncthreads();
-  if (!is_last) return;
+  if (!is_last || (a.dbg & 2)) return;
   __threadfence();
 
   // ------------------------------ phase 2: merge + gather ------------------------------
@@ -295,14 +355,25 @@ decode_kernel(DecodeArgs a) {
     const unsigned g = (unsigned)(i / K) * (unsigned)HW + idx;            // class-major global position
     return (c & 0xFFFFFFFF00000000ull) | (unsigned long long)(0xFFFFFFFFu - g);
   };
-  radix_select(n2, K, key2, hist, &ss);
+  // The merge keys are staged in shared memory when they fit (C*K <= key_cap): every radix pass then reads them at
+  // shared-memory latency; from L2 (one dependent round trip per 512 keys per pass) the merge of one image took ~35 us,
+  // serialised at the tail of the launch.
+  unsigned long long* skeys = reinterpret_cast<unsigned long long*>(smem_raw);
+  const bool keys_in_smem = n2 <= a.key_cap;
+  if (keys_in_smem) {
+    for (int i = tid; i < n2; i += DT) skeys[i] = key2(i);
+    __syncthreads();
+  }
+  auto key2s = [&](int i) -> unsigned long long { return skeys[i]; };
+  if (keys_in_smem) radix_select(n2, K, key2s, hist, &ss);
+  else radix_select(n2, K, key2, hist, &ss);
   if (tid == 0) sel_n = 0;
   for (int i = tid; i < a.kpad; i += DT) sel[i] = 0ull;
   __syncthreads();
   {
     const unsigned long long prefix = ss.prefix, mask = ss.mask;
     for (int i = tid; i < n2; i += DT) {
-      const unsigned long long key = key2(i);
+      const unsigned long long key = keys_in_smem ? skeys[i] : key2(i);
       if ((key & mask) >= prefix) {
         const int slot = atomicAdd(&sel_n, 1);
         if (slot < MAXK) sel[slot] = key;
@@ -457,17 +528,27 @@ extern "C" int ct_decode(const ct_decode_desc* d, void* stream) {
   int kpad = 1;
   while (kpad < d->K) kpad <<= 1;
   a.kpad = kpad;
+  static const int dec_dbg = getenv("CTB_DEC_DEBUG") ? atoi(getenv("CTB_DEC_DEBUG")) : 0;
+  a.dbg = dec_dbg;
   const int HW = d->H * d->W, K = d->K, J = a.d.J;
   CT_REQUIRE((long long)d->C * HW < (1ll << 31), "C*H*W must stay below 2^31 (class-major positions in the merge keys)");
-  size_t smem1 = (size_t)PEAK_CAP * 8;
+  static const int dec_bulk = getenv("CTB_DEC_BULK") ? atoi(getenv("CTB_DEC_BULK")) : 1;
+  a.bulk = (dec_bulk && (size_t)HW * 4 <= PLANE_CAP && (d->W & 3) == 0) ? 1 : 0;      // else: register-streamed planes
+  size_t smem1 = (size_t)PEAK_CAP * 8 + (a.bulk ? PLANE_CAP : 0);
   size_t smem2 = (size_t)(7 * K + 4 * J * K) * 4;
   size_t smem = smem1 > smem2 ? smem1 : smem2;
+  a.key_cap = (int)(smem / 8);
   if (smem > 200 * 1024)
     return fail(CT_ERR_UNSUPPORTED, "ct_decode: K x joints of %s%ld floats exceed the shared-memory scratch of the pose "
                                     "refinement", "", (long)(4 * J * K));
   cudaStream_t st = (cudaStream_t)stream;
-  CT_CUDA_OK(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(d->C + J, d->B);
-  decode_kernel<<<grid, DT, smem, st>>>(a);
+  if (a.bulk) {
+    CT_CUDA_OK(cudaFuncSetAttribute(decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    decode_kernel<true><<<grid, DT, smem, st>>>(a);
+  } else {
+    CT_CUDA_OK(cudaFuncSetAttribute(decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    decode_kernel<false><<<grid, DT, smem, st>>>(a);
+  }
   return after_launch();
 }

@@ -9,7 +9,7 @@ dump _ZN3ctb14conv_tc_kernelILb0EEEvNS_6TcArgsE14CUtensorMap_st profiles/r02_sas
 dump _ZN3ctb14conv_tc_kernelILb1EEEvNS_6TcArgsE14CUtensorMap_st profiles/r02_sass_tc_x3.txt
 dump _ZN3ctb16conv_halo_kernelENS_8HaloArgsE14CUtensorMap_st profiles/r02_sass_halo.txt
 dump _ZN3ctb18dcn_persist_kernelENS_6TcArgsEi14CUtensorMap_st profiles/r02_sass_dcn_persist.txt
-dump _ZN3ctb13decode_kernelENS_10DecodeArgsE profiles/r02_sass_decode.txt
+dump _ZN3ctb13decode_kernelILb1EEEvNS_10DecodeArgsE profiles/r02_sass_decode.txt
 dump _ZN3ctb17track_step_kernelENS_9TrackArgsE profiles/r02_sass_track.txt
 {
   echo "# Blackwell-native mnemonics per kernel (cuobjdump -sass of $SO; tools/sass_dump.sh)"
