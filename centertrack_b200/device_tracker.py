@@ -5,7 +5,8 @@
 stream never returns to the host between frames: records(t) -> tracks(t) -> pre_hm(t+1) are all device-resident and
 CUDA-graph capturable (fixed launch shapes).
 
-Greedy association only (`--hungarian` / `--public_det` are out of scope, like centertrack_b200.tracker).
+Greedy association only: `--hungarian` / `--public_det` streams use the host tracker (centertrack_b200.tracker,
+`Detector.run`); this class refuses them rather than silently tracking differently.
 Results are rows of CT_TRK_FLOATS fp32 (score, class, ct, tracking, bbox, tracking_id, age, active) in the
 reference's output order (matched detections, new tracks, coasting tracks); `results()` turns a host copy into the
 reference's list of dicts.
@@ -25,7 +26,8 @@ class DeviceTracker(object):
     """centers/scales: per-stream (c, s) of the source rectangle (Detector._input_geometry); default = a source image
     of exactly the network input size (the synthetic benchmark streams)."""
     if getattr(opt, 'hungarian', False) or getattr(opt, 'public_det', False):
-      raise NotImplementedError('--hungarian / --public_det are outside the B200 hot-path scope')
+      raise NotImplementedError('the device tracker is greedy-only: --hungarian / --public_det run on the host '
+                                '(centertrack_b200.tracker.Tracker via Detector.run)')
     self.opt, self.B, self.K, self.F = opt, B, K, rec_floats
     self.inp_h, self.inp_w = inp_h, inp_w
     self.device = torch.device(device)

@@ -147,3 +147,40 @@ def synthetic_inputs(B, H, W, seed=317, n_blobs=20):
       blob = torch.exp(-((xs - cx) ** 2 + (ys - cy) ** 2) / (2 * sig * sig))
       hm[b, 0] = torch.maximum(hm[b, 0], blob)
   return img, pre, hm
+
+
+def synthetic_track_stream(seed, frames=6, crowd=40):
+  """Seeded post-processed detections of a crowded stream for the association tests and goldens (no network involved):
+  per frame a score-sorted list of {score, class, ct, tracking, bbox} in image coordinates plus a list of public
+  detections ({ct}) jittered around a subset of them (the MOT public-detection protocol, tracker.py:83-103).
+  One frame of every stream is empty, objects persist with small motion so that matches, births, rejected
+  assignments and coasting tracks all occur."""
+  import numpy as np
+  rng = np.random.RandomState(7000 + seed)
+  n_obj = int(rng.randint(crowd // 2, crowd))
+  ct = rng.uniform(10, 300, (n_obj, 2))
+  wh = rng.uniform(4, 50, (n_obj, 2))
+  cls = rng.randint(1, 4, n_obj)
+  out = []
+  for f in range(frames):
+    move = rng.normal(0, 4, (n_obj, 2))
+    ct = ct + move
+    seen = rng.uniform(size=n_obj) < (0.0 if f == 3 and seed % 2 == 0 else 0.8)
+    dets = []
+    for i in np.nonzero(seen)[0]:
+      c = (ct[i] + rng.normal(0, 0.5, 2)).astype(np.float32)
+      w, h = wh[i] * rng.uniform(0.9, 1.1, 2)
+      dets.append({'score': float(np.float32(rng.uniform(0.15, 1.0))), 'class': int(cls[i]),
+                   'ct': c, 'tracking': (-move[i] + rng.normal(0, 1.5, 2)).astype(np.float32),
+                   'bbox': np.array([c[0] - w / 2, c[1] - h / 2, c[0] + w / 2, c[1] + h / 2], np.float32)})
+    for _ in range(int(rng.randint(0, 6))):        # clutter: detections that belong to no object
+      c = rng.uniform(0, 310, 2).astype(np.float32)
+      w, h = rng.uniform(3, 30, 2)
+      dets.append({'score': float(np.float32(rng.uniform(0.15, 0.6))), 'class': int(rng.randint(1, 4)),
+                   'ct': c, 'tracking': rng.normal(0, 3, 2).astype(np.float32),
+                   'bbox': np.array([c[0] - w / 2, c[1] - h / 2, c[0] + w / 2, c[1] + h / 2], np.float32)})
+    dets.sort(key=lambda d: -d['score'])
+    pub = [{'ct': (d['ct'] + d['tracking'] + rng.normal(0, 2.0, 2)).astype(np.float32)}
+           for d in dets if rng.uniform() < 0.6]
+    out.append((dets, pub))
+  return out

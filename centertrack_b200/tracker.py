@@ -1,7 +1,8 @@
-"""Greedy displacement association with the reference's surface (utils/tracker.py:6-138):
+"""Displacement association with the reference's surface (utils/tracker.py:6-138):
 Tracker(opt).init_track / step / reset, attributes .tracks / .id_count; mutates and returns the
-same result dicts.  Hungarian matching and the MOT public-detection mode are out of scope (not in any
-benchmark config) and raise."""
+same result dicts.  Greedy matching (the default, and what `ct_track_step` runs on the device), `--hungarian`
+(tracker.py:52-72; the reference imports sklearn's removed `linear_assignment`, here scipy's
+`linear_sum_assignment` solves the same problem) and the MOT `--public_det` birth rule (tracker.py:83-103)."""
 import numpy as np
 
 _BLOCKED = 1e18      # cost of a forbidden (detection, track) pair
@@ -21,6 +22,19 @@ def greedy_assignment(dist):
   return np.array(pairs, np.int32).reshape(-1, 2)
 
 
+def hungarian_assignment(cost):
+  """tracker.py:52-55,63-72: minimum-cost assignment over the gated cost matrix (blocked pairs clamped to exactly
+  _BLOCKED so that they all weigh the same); pairs the solver was forced to take through a blocked cell are handed
+  back as `rejected` -- the reference appends those detections / tracks to its unmatched lists AFTER the naturally
+  unmatched ones, which fixes the order new ids are given in."""
+  from scipy.optimize import linear_sum_assignment
+  cost[cost > _BLOCKED] = _BLOCKED
+  rows, cols = linear_sum_assignment(cost)
+  keep = cost[rows, cols] <= _TAKEN if len(rows) else np.zeros(0, bool)
+  pairs = np.stack([rows, cols], 1).astype(np.int64).reshape(-1, 2)
+  return pairs[keep], pairs[~keep], pairs
+
+
 def _box_area(box):
   return (box[2] - box[0]) * (box[3] - box[1])
 
@@ -28,8 +42,6 @@ def _box_area(box):
 class Tracker(object):
 
   def __init__(self, opt):
-    if getattr(opt, 'hungarian', False) or getattr(opt, 'public_det', False):
-      raise NotImplementedError('--hungarian / --public_det are outside the B200 hot-path scope')
     self.opt = opt
     self.reset()
 
@@ -67,17 +79,47 @@ class Tracker(object):
     blocked = (cost > trk_area[None, :]) | (cost > det_area[:, None]) | (det_cls[:, None] != trk_cls[None, :])
     return cost + blocked * _BLOCKED
 
+  def _public_births(self, results, pred, unmatched, det_area, public_det):
+    """tracker.py:83-103 (MOT public-detection protocol): a track may only start on a provided detection.  Each public
+    detection, in order, claims the unmatched detection whose predicted previous centre is nearest to it, if that is
+    closer than the detection's own box area; a claimed detection is out of the pool whether or not it is confident
+    enough to be born."""
+    pub = np.array([d['ct'] for d in public_det], np.float32).reshape(1, -1, 2)
+    cost = ((pred.reshape(-1, 1, 2) - pub) ** 2).sum(axis=2)                   # [n, p] float32
+    free = np.zeros(len(results), bool)
+    free[list(unmatched)] = True
+    cost[~free] = _BLOCKED
+    born = []
+    for j in range(cost.shape[1]):
+      i = int(cost[:, j].argmin())
+      if cost[i, j] < det_area[i]:
+        cost[i, :] = _BLOCKED
+        if results[i]['score'] > self.opt.new_thresh:
+          born.append(self._birth(results[i]))
+    return born
+
   def step(self, results, public_det=None):
-    pairs = greedy_assignment(self._gated_cost(results))
+    n, m = len(results), len(self.tracks)
+    cost = self._gated_cost(results)
+    if getattr(self.opt, 'hungarian', False):
+      pairs, rejected, taken = hungarian_assignment(cost)
+    else:
+      pairs = taken = greedy_assignment(cost.copy())
+      rejected = pairs[:0]
     out = []
     for det, trk in pairs:                       # continued tracks inherit the id; `active` counts the streak
       item, old = results[det], self.tracks[trk]
       item.update(tracking_id=old['tracking_id'], age=1, active=old['active'] + 1)
       out.append(item)
-    fresh = set(range(len(results))) - set(pairs[:, 0].tolist())
-    out.extend(self._birth(results[i]) for i in sorted(fresh) if results[i]['score'] > self.opt.new_thresh)
-    lost = set(range(len(self.tracks))) - set(pairs[:, 1].tolist())
-    for i in sorted(lost):                       # unmatched tracks coast while younger than max_age
+    fresh = sorted(set(range(n)) - set(taken[:, 0].tolist())) + rejected[:, 0].tolist()
+    lost = sorted(set(range(m)) - set(taken[:, 1].tolist())) + rejected[:, 1].tolist()
+    if getattr(self.opt, 'public_det', False) and fresh:
+      pred = np.array([np.asarray(r['ct']) + np.asarray(r['tracking']) for r in results], np.float32).reshape(n, 2)
+      det_area = np.array([_box_area(r['bbox']) for r in results], np.float32)
+      out.extend(self._public_births(results, pred, fresh, det_area, public_det))
+    else:
+      out.extend(self._birth(results[i]) for i in fresh if results[i]['score'] > self.opt.new_thresh)
+    for i in lost:                               # unmatched tracks coast while younger than max_age
       old = self.tracks[i]
       if old['age'] < self.opt.max_age:
         old['age'] += 1

@@ -231,6 +231,40 @@ def gen_post_track():
   print('post_track', len(data), 'arrays')
 
 
+TRACK_MODES = [  # (name, extra opts argv)
+    ('greedy_age2', ['--max_age', '2']),
+    ('hungarian', ['--hungarian']),
+    ('hungarian_age2', ['--hungarian', '--max_age', '2']),
+    ('public', ['--public_det']),
+    ('public_hungarian_age2', ['--public_det', '--hungarian', '--max_age', '2'])]
+
+
+def gen_track_modes():
+  """Crowded seeded streams (synthetic.synthetic_track_stream) through the reference's Tracker in its other modes:
+  --hungarian (sklearn's removed linear_assignment is stood in for by scipy's linear_sum_assignment, ref_harness),
+  --public_det, --max_age coasting."""
+  import copy
+  from utils.tracker import Tracker
+  data = {}
+  for name, extra in TRACK_MODES:
+    for seed in range(4):
+      opt = rh.make_opt('coco_tracking', extra=['--track_thresh', '0.2', '--new_thresh', '0.3'] + extra)
+      tracker = Tracker(opt)
+      for f, (dets, pub) in enumerate(wt.synthetic_track_stream(seed)):
+        dets = copy.deepcopy(dets)
+        for d in dets:                              # the reference adds lists: ct + tracking must be array-like
+          d['ct'] = np.asarray(d['ct']); d['tracking'] = np.asarray(d['tracking'])
+        if f == 0:
+          tracker.init_track([])
+        out = tracker.step(dets, pub)
+        rows = [[o['tracking_id'], o['age'], o['active'], o['class'], o['score']] + list(map(float, o['bbox']))
+                for o in out]
+        data['%s.s%d.f%d' % (name, seed, f)] = np.array(rows, np.float64).reshape(-1, 9)
+        data['%s.s%d.f%d.n' % (name, seed, f)] = np.array([len(out), tracker.id_count])
+  np.savez_compressed(os.path.join(OUT, 'track_modes.npz'), **data)
+  print('track_modes', len(data), 'arrays')
+
+
 HOST_CASES = [  # (name, extra opts argv, image (h, w), input_meta has calib)
     ('fix_res', ['--input_h', '128', '--input_w', '160'], (120, 200), False),
     ('fix_res_tall', ['--input_h', '160', '--input_w', '128'], (333, 210), True),
@@ -324,7 +358,7 @@ def gen_host():
 if __name__ == '__main__':
   os.makedirs(OUT, exist_ok=True)
   torch.manual_seed(0)
-  which = sys.argv[1:] or ['net', 'e2e', 'decode', 'post', 'host', 'opts', 'flip']
+  which = sys.argv[1:] or ['net', 'e2e', 'decode', 'post', 'track', 'host', 'opts', 'flip']
   rh.install()
   if 'net' in which:
     gen_net()
@@ -332,6 +366,8 @@ if __name__ == '__main__':
     gen_decode()
   if 'post' in which:
     gen_post_track()
+  if 'track' in which:
+    gen_track_modes()
   if 'e2e' in which:
     gen_e2e()
   if 'host' in which:
