@@ -6,8 +6,11 @@
 (dla.py:594-617 + base_model.py:14-65), so reference checkpoints load key-for-key (including the two
 dead `base.level{3,4}.project.*` tensors and BatchNorm's `num_batches_tracked`), but holds no PyTorch
 compute: `forward` hands the state_dict to a `DLA34Engine` plan of libctb200 launches.
-Only `dla_34` (the default --arch, opts.py:82) is built -- with any `--dla_node` (dcn | conv | gcn, dla.py:588-592);
-other archs raise.
+Archs: `dla_34` (the default --arch, opts.py:82) with any `--dla_node` (dcn | conv | gcn, dla.py:588-592), and
+`generic` with `--backbone dla34 --neck dlaup` (generic_network.py:29-107 over backbones/dla.py + necks/dlaup.py): the
+same graph under the state-dict names `backbone.*` / `neck.{dla_up,ida_up}.*`, so it runs the same engine plan.
+`resdcn` / `res` / `dlav0` and the resnet / mobilenet backbones or the msraup neck raise: their `BaseModel.forward`
+has no `imgpre2feats` (resdcn.py:192-206), i.e. they cannot take the tracking inputs this path exists for.
 """
 import torch
 import torch.nn as nn
@@ -121,45 +124,54 @@ def _ida(o, channels, up_f, node_type=(_deform, _deform)):    # IDAUp keys: proj
   return m
 
 
-class DLASegB200(nn.Module):
-  """State-dict-compatible stand-in for DLASeg(34, heads, head_convs, opt)."""
+def _dla34_backbone(opt):
+  """DLA-34 `base` (dla.py:231-267 == backbones/dla.py:223-265): stems, level0..5."""
+  base = _Holder()
+  base.base_layer = _stem(3, 16)
+  base.level0 = _conv_level(16, 16)
+  base.level1 = _conv_level(16, 32)
+  base.level2 = _tree(1, 32, 64, level_root=False)
+  base.level3 = _tree(2, 64, 128, level_root=True)
+  base.level4 = _tree(2, 128, 256, level_root=True)
+  base.level5 = _tree(1, 256, 512, level_root=True)
+  if opt is None or getattr(opt, 'pre_img', False):
+    base.pre_img_layer = _stem(3, 16)
+  if opt is None or getattr(opt, 'pre_hm', False):
+    base.pre_hm_layer = _stem(1, 16)
+  return base
 
-  def __init__(self, num_layers, heads, head_convs, opt=None):
-    super(DLASegB200, self).__init__()
-    if num_layers != 34:
-      raise NotImplementedError('only DLA-34 (arch dla_34) is on the B200 hot path')
-    node_type = DLA_NODE[getattr(opt, 'dla_node', 'dcn') if opt is not None else 'dcn']      # dla.py:588-592
+
+def _dlaup_neck(node_type):
+  """(dla_up, ida_up) of dla.py:549-566,606-617 == necks/dlaup.py:139-190.
+  DLAUp: ida_0 sees [256,512], ida_1 [128,256,256], ida_2 [64,128,128,128]."""
+  ch = [16, 32, 64, 128, 256, 512]
+  dla_up = _Holder()
+  channels, in_ch = ch[2:], list(ch[2:])
+  scales = [1, 2, 4, 8]
+  for i in range(3):
+    j = -i - 2
+    setattr(dla_up, 'ida_%d' % i, _ida(channels[j], in_ch[j:], [s // scales[j] for s in scales[j:]], node_type))
+    scales[j + 1:] = [scales[j]] * len(scales[j + 1:])
+    in_ch[j + 1:] = [channels[j]] * len(in_ch[j + 1:])
+  return dla_up, _ida(64, ch[2:5], [1, 2, 4], node_type)
+
+
+class _B200Net(nn.Module):
+  """What the two archs share: the head modules (base_model.py:23-65 == generic_network.py:47-89), the engine cache
+  and `forward`.  Subclasses register the trunk under the reference's names and say how those names map onto the
+  engine's (`_engine_state_dict`)."""
+
+  def _common_init(self, heads, opt):
     self.opt = opt
     self.heads = heads
     self.num_stacks = 1
+    self.precision = getattr(opt, 'b200_precision', 'bf16') if opt is not None else 'bf16'
+    self._engines = {}
+    return DLA_NODE[getattr(opt, 'dla_node', 'dcn') if opt is not None else 'dcn']      # dla.py:588-592
+
+  def _add_heads(self, heads, head_convs, opt):
     head_kernel = getattr(opt, 'head_kernel', 3) if opt is not None else 3
     prior_bias = getattr(opt, 'prior_bias', -4.6) if opt is not None else -4.6
-    ch = [16, 32, 64, 128, 256, 512]
-    base = _Holder()
-    base.base_layer = _stem(3, 16)
-    base.level0 = _conv_level(16, 16)
-    base.level1 = _conv_level(16, 32)
-    base.level2 = _tree(1, 32, 64, level_root=False)
-    base.level3 = _tree(2, 64, 128, level_root=True)
-    base.level4 = _tree(2, 128, 256, level_root=True)
-    base.level5 = _tree(1, 256, 512, level_root=True)
-    if opt is None or getattr(opt, 'pre_img', False):
-      base.pre_img_layer = _stem(3, 16)
-    if opt is None or getattr(opt, 'pre_hm', False):
-      base.pre_hm_layer = _stem(1, 16)
-    self.base = base
-    # DLAUp (dla.py:549-566): ida_0 sees [256,512], ida_1 [128,256,256], ida_2 [64,128,128,128]
-    dla_up = _Holder()
-    channels, in_ch = ch[2:], list(ch[2:])
-    scales = [1, 2, 4, 8]
-    for i in range(3):
-      j = -i - 2
-      setattr(dla_up, 'ida_%d' % i, _ida(channels[j], in_ch[j:], [s // scales[j] for s in scales[j:]], node_type))
-      scales[j + 1:] = [scales[j]] * len(scales[j + 1:])
-      in_ch[j + 1:] = [channels[j]] * len(in_ch[j + 1:])
-    self.dla_up = dla_up
-    self.ida_up = _ida(64, ch[2:5], [1, 2, 4], node_type)
-    # heads (base_model.py:23-65)
     for head in heads:
       classes, hc = heads[head], head_convs[head]
       if len(hc) > 0:
@@ -182,13 +194,15 @@ class DLASegB200(nn.Module):
         else:
           nn.init.constant_(fc.bias, 0)
       setattr(self, head, fc)
-    self.precision = getattr(opt, 'b200_precision', 'bf16') if opt is not None else 'bf16'
-    self._engines = {}
+
+  def _engine_state_dict(self):
+    """The module's tensors under the names the engine plan uses (DLASeg's: base.*, dla_up.*, ida_up.*, <head>.*)."""
+    return self.state_dict()
 
   # -- engine cache ---------------------------------------------------------------------------
   def _load_from_state_dict(self, *args, **kwargs):
     self._engines = {}
-    return super(DLASegB200, self)._load_from_state_dict(*args, **kwargs)
+    return super(_B200Net, self)._load_from_state_dict(*args, **kwargs)
 
   def invalidate(self):
     self._engines = {}
@@ -209,7 +223,7 @@ class DLASegB200(nn.Module):
     eng = self._engines.pop(key, None)
     if eng is None:
       depth_scale = getattr(self.opt, 'depth_scale', 1.0) if self.opt is not None else 1.0
-      eng = DLA34Engine(self.state_dict(), self.heads, B, H, W, precision=precision, device=device,
+      eng = DLA34Engine(self._engine_state_dict(), self.heads, B, H, W, precision=precision, device=device,
                         depth_scale=depth_scale, dla_node=getattr(self.opt, 'dla_node', 'dcn') if self.opt is not None else 'dcn')
       while len(self._engines) >= self.MAX_ENGINES:           # --keep_res / --fix_short on variable-size inputs
         self._engines.pop(next(iter(self._engines)))
@@ -234,16 +248,71 @@ class DLASegB200(nn.Module):
     return [z]
 
 
+class DLASegB200(_B200Net):
+  """State-dict-compatible stand-in for DLASeg(34, heads, head_convs, opt) (dla.py:576-640)."""
+
+  def __init__(self, num_layers, heads, head_convs, opt=None):
+    super(DLASegB200, self).__init__()
+    if num_layers != 34:
+      raise NotImplementedError('only DLA-34 (arch dla_34) is on the B200 hot path')
+    node_type = self._common_init(heads, opt)
+    self.base = _dla34_backbone(opt)
+    self.dla_up, self.ida_up = _dlaup_neck(node_type)
+    self._add_heads(heads, head_convs, opt)
+
+
+class _DLAUpNeck(_Holder):                     # necks/dlaup.py:170-190: `neck.dla_up.*`, `neck.ida_up.*`
+  pass
+
+
+class GenericNetworkB200(_B200Net):
+  """State-dict-compatible stand-in for GenericNetwork(num_layers, heads, head_convs, opt=opt) with
+  `--backbone dla34 --neck dlaup` (generic_network.py:29-107).  backbones/dla.py's DLA and necks/dlaup.py's DLASeg are
+  the `base` / `dla_up` + `ida_up` of dla.py under other names (the forward is the same graph: x = base_layer(img)
+  + pre_img_layer(pre) + pre_hm_layer(hm), level0..5, DLAUp, clone, IDAUp, take the last), so the tensors are handed
+  to the same engine plan with `backbone.` -> `base.`, `neck.dla_up.` -> `dla_up.`, `neck.ida_up.` -> `ida_up.`.
+  Note opts.py:295: `head_conv` defaults to 64 (not 256) when the arch name has no 'dla' in it."""
+
+  RENAME = (('backbone.', 'base.'), ('neck.dla_up.', 'dla_up.'), ('neck.ida_up.', 'ida_up.'))
+
+  def __init__(self, num_layers, heads, head_convs, num_stacks=1, opt=None):
+    super(GenericNetworkB200, self).__init__()
+    backbone = getattr(opt, 'backbone', 'dla34') if opt is not None else 'dla34'
+    neck = getattr(opt, 'neck', 'dlaup') if opt is not None else 'dlaup'
+    if backbone != 'dla34' or neck != 'dlaup':
+      raise NotImplementedError('generic arch: only --backbone dla34 --neck dlaup is on the B200 hot path '
+                                '(got %s / %s)' % (backbone, neck))
+    print('Using generic model with backbone {} and neck {}'.format(backbone, neck))
+    node_type = self._common_init(heads, opt)
+    self.backbone = _dla34_backbone(opt)
+    self.backbone.channels = [16, 32, 64, 128, 256, 512]
+    self.neck = _DLAUpNeck()
+    self.neck.dla_up, self.neck.ida_up = _dlaup_neck(node_type)
+    self.neck.out_channel = 64
+    self._add_heads(heads, head_convs, opt)
+
+  def _engine_state_dict(self):
+    out = {}
+    for k, v in self.state_dict().items():
+      for a, b in self.RENAME:
+        if k.startswith(a):
+          k = b + k[len(a):]
+          break
+      out[k] = v
+    return out
+
+
 def _unsupported(name):
   def make(*a, **k):
-    raise NotImplementedError('arch %r is outside the B200 hot path (dla_34 only)' % name)
+    raise NotImplementedError('arch %r is outside the B200 hot path (dla_34, or generic with --backbone dla34 '
+                              '--neck dlaup): it has no imgpre2feats, i.e. no tracking inputs' % name)
   return make
 
 
 _network_factory = {
     'dla': DLASegB200,
     'resdcn': _unsupported('resdcn'), 'res': _unsupported('res'),
-    'dlav0': _unsupported('dlav0'), 'generic': _unsupported('generic'),
+    'dlav0': _unsupported('dlav0'), 'generic': GenericNetworkB200,
 }
 
 

@@ -23,6 +23,9 @@ class opts(object):
     a('--seed', type=int, default=317)
     a('--arch', default='dla_34')
     a('--dla_node', default='dcn')
+    a('--backbone', default='dla34')           # --arch generic (generic_network.py:13-22)
+    a('--neck', default='dlaup')
+    a('--msra_outchannel', type=int, default=256)
     a('--head_conv', type=int, default=-1)
     a('--num_head_conv', type=int, default=1)
     a('--head_kernel', type=int, default=3)

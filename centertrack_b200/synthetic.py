@@ -44,8 +44,20 @@ def calib_path(seed):
   return os.path.join(_DATA, 'bn_calib_seed%d.npz' % seed)
 
 
-def make_state_dict(template, seed=317, hm_scale=1.0, calibrated=True):
-  """template: {key: tensor} (only shapes/dtypes are read).  Returns a new state_dict."""
+def make_state_dict(template, seed=317, hm_scale=1.0, calibrated=True, rename=()):
+  """template: {key: tensor} (only shapes/dtypes are read).  Returns a new state_dict.
+  rename: ((prefix, dla_prefix), ...) for modules that hold the DLASeg graph under other names (--arch generic:
+  `backbone.` = `base.`, `neck.dla_up.` = `dla_up.`, ...): tensors are generated (and BN statistics looked up) under
+  the DLASeg name, so both archs get the SAME weights, and returned under the template's own keys."""
+  if rename:
+    def canon(k):
+      for a, b in rename:
+        if k.startswith(a):
+          return b + k[len(a):]
+      return k
+    names = {k: canon(k) for k in template}
+    sd = make_state_dict({names[k]: v for k, v in template.items()}, seed, hm_scale, calibrated)
+    return {k: sd[names[k]] for k in template}
   ck = (tuple(sorted((k, tuple(v.shape)) for k, v in template.items())), seed, hm_scale, calibrated)
   if ck in _cache:
     return {k: v.clone() for k, v in _cache[ck].items()}

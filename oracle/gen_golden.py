@@ -76,6 +76,49 @@ def gen_net():
     print('net', cfg, node, {k: v.shape for k, v in data.items() if k != 'keys'})
 
 
+GENERIC_RENAME = (('backbone.', 'base.'), ('neck.dla_up.', 'dla_up.'), ('neck.ida_up.', 'ida_up.'))
+
+
+def gen_generic():
+  """--arch generic --backbone dla34 --neck dlaup (generic_network.py:29-107): the reference's GenericNetwork on the
+  synthetic checkpoint (same tensors as the dla_34 goldens, generated under the DLASeg names), with its own default
+  head width (64: opts.py:295) and with --head_conv 256, where its outputs must coincide with DLASeg's."""
+  rh.no_pretrained_download()
+  img, pre, hm = wt.synthetic_inputs(1, *SMALL_HW)
+  inv = {b: a for a, b in GENERIC_RENAME}
+  def generic_name(n):
+    for b, a in inv.items():
+      if n.startswith(b):
+        return a + n[len(b):]
+    return n
+  data = {}
+  for tag, extra in (('hc64', []), ('hc256', ['--head_conv', '256'])):
+    opt, model = rh.build_reference_model('coco_tracking', input_hw=SMALL_HW, extra=['--arch', 'generic'] + extra)
+    sd = wt.make_state_dict(model.state_dict(), 317, rename=GENERIC_RENAME)
+    model.load_state_dict(sd)
+    acts, hooks = {}, []
+    mods = dict(model.named_modules())
+    for name in STAGES:
+      hooks.append(mods[generic_name(name)].register_forward_hook(
+          lambda m, i, o, name=name: acts.__setitem__(name, o.detach().clone())))
+    with torch.no_grad():
+      out = model(img, pre, hm)[-1]
+    for h in hooks:
+      h.remove()
+    data.update({'%s.head.%s' % (tag, k): v.numpy() for k, v in out.items()})
+    data.update({'%s.stage.%s' % (tag, k): v.numpy() for k, v in acts.items()})
+    data[tag + '.keys'] = np.array(sorted(sd.keys()))
+    data[tag + '.head_conv'] = np.array([opt.head_conv[h][0] for h in opt.heads])
+    if tag == 'hc256':       # same graph, same tensors as DLASeg(34): the two reference modules must agree
+      opt2, dla = rh.build_reference_model('coco_tracking', input_hw=SMALL_HW)
+      dla.load_state_dict(wt.make_state_dict(dla.state_dict(), 317))
+      with torch.no_grad():
+        ref = dla(img, pre, hm)[-1]
+      data['hc256.max_abs_diff_vs_dla_34'] = np.array([float((out[k] - ref[k]).abs().max()) for k in out])
+  np.savez_compressed(os.path.join(OUT, 'net_generic_coco_tracking_64x96.npz'), **data)
+  print('generic', {k: v.shape for k, v in data.items() if 'head.' in k}, data['hc256.max_abs_diff_vs_dla_34'])
+
+
 E2E_CASES = [  # (file stem, cfg, (H, W), batch the frame is cut from, frame index, input seed)
     ('e2e_coco_tracking_512', 'coco_tracking', (512, 512), 1, 0, 317),
     ('e2e_coco_tracking_512_b32f0', 'coco_tracking', (512, 512), 32, 0, 4242),      # the shape bench.py runs:
@@ -358,10 +401,12 @@ def gen_host():
 if __name__ == '__main__':
   os.makedirs(OUT, exist_ok=True)
   torch.manual_seed(0)
-  which = sys.argv[1:] or ['net', 'e2e', 'decode', 'post', 'track', 'host', 'opts', 'flip']
+  which = sys.argv[1:] or ['net', 'generic', 'e2e', 'decode', 'post', 'track', 'host', 'opts', 'flip']
   rh.install()
   if 'net' in which:
     gen_net()
+  if 'generic' in which:
+    gen_generic()
   if 'decode' in which:
     gen_decode()
   if 'post' in which:

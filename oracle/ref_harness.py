@@ -145,6 +145,15 @@ def install():
   _installed = True
 
 
+def no_pretrained_download():
+  """--arch generic builds its backbone with `dla34(opt=opt)` whose `pretrained=True` default fetches ImageNet weights
+  from dl.yf.io (backbones/dla.py:362-371,305-316; SURVEY hazard H7) -- there is no network here and every weight
+  is overwritten by the synthetic checkpoint anyway, so the download (and only the download) is skipped."""
+  install()
+  import model.networks.backbones.dla as bdla
+  bdla.DLA.load_pretrained_model = lambda self, *a, **k: None
+
+
 TASK_ARGS = {
     # name -> (task, extra argv)   (BASELINE.json configs 1..5)
     'coco_tracking': ('tracking', []),

@@ -27,7 +27,7 @@ def make_model(cfg, seed=317, extra=()):
   from centertrack_b200.model import create_model
   opt = make_opt(cfg, extra)
   m = create_model(opt.arch, opt.heads, opt.head_conv, opt=opt)
-  sd = wt.make_state_dict(m.state_dict(), seed)
+  sd = wt.make_state_dict(m.state_dict(), seed, rename=getattr(m, 'RENAME', ()))
   m.load_state_dict(sd)
   return opt, m, sd
 

@@ -352,3 +352,53 @@ def test_hungarian_rejects_forced_pairs_and_orders_births_like_the_reference():
     out = t.step([mk(200, 200, 1, 0.9), mk(11, 10, 1, 0.8), mk(50, 50, 2, 0.7)])
     assert [(o['tracking_id'], o['active']) for o in out] == [(1, 2), (3, 1), (4, 1)]
     assert [float(o['ct'][0]) for o in out] == [11.0, 50.0, 200.0]    # natural unmatched (det 2) before the rejected det 0
+
+
+@pytest.mark.parametrize('tag,extra', [('hc64', []), ('hc256', ['--head_conv', '256'])])
+def test_generic_arch_oracle_and_product_keys_match_reference_golden(tag, extra, golden_dir):
+  """--arch generic --backbone dla34 --neck dlaup (generic_network.py:29-107): state-dict keys of the product module
+  equal the reference GenericNetwork's, the head width follows opts.py:295 (64 unless --head_conv), and the oracle
+  restatement reproduces the reference's outputs and stages."""
+  g = np.load(os.path.join(golden_dir, 'net_generic_coco_tracking_64x96.npz'))
+  opt, model, sd = make_model('coco_tracking', extra=['--arch', 'generic'] + extra)
+  assert sorted(sd.keys()) == list(g[tag + '.keys'])
+  assert [opt.head_conv[h][0] for h in opt.heads] == list(g[tag + '.head_conv'])
+  img, pre, hm = wt.synthetic_inputs(1, 64, 96)
+  trace = {}
+  out = co.GenericDLA34Oracle(sd, opt.heads).forward(img, pre, hm, trace=trace)
+  for k in out:
+    assert np.abs(out[k].numpy() - g['%s.head.%s' % (tag, k)]).max() < 1e-3, k
+  for k in [x for x in g.files if x.startswith(tag + '.stage.')]:
+    name = k[len(tag + '.stage.'):]
+    key = 'feat' if name == 'ida_up.node_2' else name
+    assert np.abs(trace[key].numpy() - g[k]).max() < 1e-3 * max(1.0, np.abs(g[k]).max()), name
+
+
+def test_generic_arch_is_the_dla34_graph_under_other_names(golden_dir):
+  """With --head_conv 256 the reference's GenericNetwork and DLASeg(34) agree exactly on the same tensors (recorded by
+  the generator), the generic golden equals the dla_34 golden, and the product hands its engine the very state dict
+  the dla_34 module does -- so the device plan that runs is the one the dla_34 GPU tests cover."""
+  g = np.load(os.path.join(golden_dir, 'net_generic_coco_tracking_64x96.npz'))
+  d = np.load(os.path.join(golden_dir, 'net_coco_tracking_64x96.npz'))
+  assert np.all(g['hc256.max_abs_diff_vs_dla_34'] == 0)
+  for h in ('hm', 'reg', 'wh', 'tracking'):
+    assert np.array_equal(g['hc256.head.' + h], d['head.' + h])
+  _, gen, _ = make_model('coco_tracking', extra=['--arch', 'generic', '--head_conv', '256'])
+  _, dla, sd = make_model('coco_tracking')
+  esd = gen._engine_state_dict()
+  assert list(esd) == list(sd)                       # same names, same registration order
+  assert all(torch.equal(esd[k], sd[k]) for k in sd)
+
+
+def test_unsupported_archs_raise_not_implemented():
+  from centertrack_b200.model import create_model
+  opt = make_opt('coco_tracking', ['--arch', 'generic', '--backbone', 'resnet'])
+  with pytest.raises(NotImplementedError):
+    create_model(opt.arch, opt.heads, opt.head_conv, opt=opt)
+  opt = make_opt('coco_tracking', ['--arch', 'generic', '--neck', 'msraup'])
+  with pytest.raises(NotImplementedError):
+    create_model(opt.arch, opt.heads, opt.head_conv, opt=opt)
+  for arch in ('resdcn_18', 'res_18', 'dlav0_34'):
+    opt = make_opt('coco_tracking', ['--arch', arch])
+    with pytest.raises(NotImplementedError):
+      create_model(opt.arch, opt.heads, opt.head_conv, opt=opt)
