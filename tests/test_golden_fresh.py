@@ -17,7 +17,7 @@ REF = os.environ.get('CT_REF_ROOT', '/root/reference')
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, 'src', 'lib')), reason='reference checkout not present')
 def test_committed_goldens_are_what_the_reference_produces(tmp_path, golden_dir):
   env = dict(os.environ, CT_GOLDEN_OUT=str(tmp_path))
-  r = subprocess.run([sys.executable, os.path.join(ROOT, 'oracle', 'gen_golden.py'), 'net', 'decode', 'post', 'track', 'host',
+  r = subprocess.run([sys.executable, os.path.join(ROOT, 'oracle', 'gen_golden.py'), 'net', 'generic', 'decode', 'post', 'track', 'host',
                       'opts', 'e2e', 'flip'], capture_output=True, text=True, timeout=1500, env=env)
   assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
   fresh = sorted(os.listdir(str(tmp_path)))
