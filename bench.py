@@ -336,6 +336,33 @@ def parity_at_bench_shape(runner, cfg, B, H, W, precision, wt):
   return res
 
 
+def accurate_engine_leg(model, cfg, B, H, W, opt, dev, tracking, host_img, host_hm, wt, steps=8, warmup=3):
+  """The same step on the tensor-core engine that meets north_star's 1e-3 (bf16x3: fp32 activations, bf16 hi/lo split
+  operands), device-resident timing + its parity at this shape, so that ONE bench line says "Y frames/s at the bf16
+  format's error, X frames/s within 1e-3 of the reference".  Runs after every headline measurement; a failure here is
+  reported in the key and cannot touch the numbers above it."""
+  from centertrack_b200.runner import NS, StreamRunner
+  r = StreamRunner(model, B, H, W, K=K, precision='bf16x3', device=dev, opt=opt, device_tracking=tracking)
+  for s in range(NS):
+    r.load_device_inputs(host_img[s & 1].to(dev), host_hm[s & 1].to(dev), s)
+  r.warm()
+  for _ in range(warmup):
+    r.step_device()
+  torch.cuda.synchronize(dev)
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for _ in range(steps):
+    r.step_device()
+  e1.record()
+  torch.cuda.synchronize(dev)
+  ms = e0.elapsed_time(e1) / steps
+  par = parity_at_bench_shape(r, cfg, B, H, W, 'bf16x3', wt)
+  return {'engine': 'bf16x3', 'value': B / (ms / 1000.0), 'unit': 'frames/s', 'ms_per_step': ms, 'steps': steps,
+          'warmup': warmup, 'what': 'same step (splat + network + decode + association, one CUDA graph, inputs resident) '
+          'on the tcgen05 engine with bf16 hi/lo split operands and fp32 activations',
+          'parity_worst': par['worst'] if par else None, 'tolerance': 'north_star: fp32 heat-maps / offsets within 1e-3'}
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
@@ -348,6 +375,7 @@ def main():
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-parity', action='store_true')
   ap.add_argument('--no-latency', action='store_true')
+  ap.add_argument('--no-accurate', action='store_true', help='skip the bf16x3 (<= 1e-3) engine leg of the default run')
   ap.add_argument('--host-tracking', action='store_true',
                   help='round-1 mode: pre_hm supplied by the host, no association on the device')
   args = ap.parse_args()
@@ -558,6 +586,14 @@ def main():
                'graph replay + fused decode + one D2H of the records; wall clock incl. both synchronisations',
                'reference_published_ms': 30.0, 'reference_published_on': 'Titan Xp (BASELINE.md)'}
 
+  # ---------------- the <= 1e-3 tensor-core engine on the same step (N=1, default precision only) ----------------
+  accurate = None
+  if args.precision == 'bf16' and world == 1 and not args.no_accurate:
+    try:
+      accurate = accurate_engine_leg(model, cfg, B, H, W, opt, dev, tracking, host_img, host_hm, wt)
+    except Exception as e:                                    # noqa: BLE001
+      accurate = {'engine': 'bf16x3', 'error': repr(e)}
+
   cpu = None
   if not args.no_cpu_baseline and world == 1:       # rank 0 at N=1 only
     _use_host_threads()
@@ -584,7 +620,8 @@ def main():
           'gpu_launches': int(runner.launches_per_step * args.steps),
           'decode_us': round(decode_ms * 1000, 1),
           'tracker_us': round(tracker_ms * 1000, 1) if tracker_ms is not None else None,
-          'clocks': clocks, 'roofline': roofline, 'parity': parity, 'latency': latency, 'cpu_baseline': cpu,
+          'clocks': clocks, 'roofline': roofline, 'parity': parity, 'accurate_engine': accurate, 'latency': latency,
+          'cpu_baseline': cpu,
           'check': {'top_score_frame0': float(rec_last[0, 0, 0]), 'tracks_last_step': n_tracks_last}}
   _emit(line)
   if dist is not None:
