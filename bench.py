@@ -363,6 +363,59 @@ def accurate_engine_leg(model, cfg, B, H, W, opt, dev, tracking, host_img, host_
           'parity_worst': par['worst'] if par else None, 'tolerance': 'north_star: fp32 heat-maps / offsets within 1e-3'}
 
 
+def stock_pytorch_leg(sd, heads, B, H, W, dev, wt, steps=3, warmup=2):
+  """Context, not a target: the same graph through STOCK PyTorch on the same device -- cuDNN convolutions,
+  torchvision.ops.deform_conv2d (the im2col + GEMM design of the DCNv2 op the reference calls, dla.py:513), ATen
+  max_pool2d / topk for the decode's NMS and its two top-Ks (model/utils.py:52-87) -- eager, as the reference runs.
+  The network is the oracle's functional restatement with its tensors moved to the device (the Python reference
+  itself cannot travel to the GPU box); like `cpu_baseline` it is a reported baseline (kind "port"), run after every
+  headline measurement."""
+  import contextlib
+  import torch.nn.functional as F
+  from torchvision.ops import deform_conv2d
+  sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+  import ct_oracle as co
+
+  def dcn(x, w, b, wo, bo):
+    o1, o2, m = torch.chunk(F.conv2d(x, wo, bo, 1, 1), 3, 1)
+    return deform_conv2d(x, torch.cat((o1, o2), 1).float(), w, b, 1, 1, 1, torch.sigmoid(m).float())
+
+  orc = co.DLA34Oracle(sd, heads, dcn_fn=dcn)
+  orc.sd = {k: v.to(dev) for k, v in orc.sd.items()}
+  img, pre, hm = wt.synthetic_inputs(1, H, W, seed=317)
+  rep = lambda t: t.expand(B, *t.shape[1:]).contiguous().to(dev)
+  img, pre, hm = rep(img), rep(pre), rep(hm)
+  cuda = torch.device(dev).type == 'cuda'
+
+  def step():
+    out = orc.forward(img, pre, hm)
+    heat = torch.sigmoid(out['hm'].float())
+    heat = heat * (F.max_pool2d(heat, 3, 1, 1) == heat).float()
+    b, c = heat.shape[:2]
+    sc, _ = torch.topk(heat.view(b, c, -1), K)
+    return torch.topk(sc.view(b, -1), K)[0]
+
+  res = {'kind': 'port', 'frames_per_step': B, 'steps': steps, 'warmup': warmup, 'unit': 'frames/s',
+         'what': 'oracle network restatement on the device through stock PyTorch (cuDNN, torchvision deform_conv2d) + '
+                 'ATen NMS / top-K, eager; no association',
+         'cudnn_allow_tf32': bool(torch.backends.cudnn.allow_tf32)}
+  for name, ctx in (('fp32', contextlib.nullcontext),
+                    ('bf16_autocast', lambda: torch.autocast(torch.device(dev).type, dtype=torch.bfloat16))):
+    with torch.no_grad(), ctx():
+      for _ in range(warmup):
+        step()
+      if cuda:
+        torch.cuda.synchronize(dev)
+      t0 = time.perf_counter()
+      for _ in range(steps):
+        step()
+      if cuda:
+        torch.cuda.synchronize(dev)
+      dt = time.perf_counter() - t0
+    res[name] = B * steps / dt
+  return res
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
@@ -375,6 +428,7 @@ def main():
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-parity', action='store_true')
   ap.add_argument('--no-latency', action='store_true')
+  ap.add_argument('--no-gpu-baseline', action='store_true', help='skip the stock-PyTorch-on-the-same-GPU context leg')
   ap.add_argument('--no-accurate', action='store_true', help='skip the bf16x3 (<= 1e-3) engine leg of the default run')
   ap.add_argument('--host-tracking', action='store_true',
                   help='round-1 mode: pre_hm supplied by the host, no association on the device')
@@ -594,6 +648,15 @@ def main():
     except Exception as e:                                    # noqa: BLE001
       accurate = {'engine': 'bf16x3', 'error': repr(e)}
 
+  # ---------------- context: the same graph through stock PyTorch / cuDNN on this GPU (N=1 only) ----------------
+  gpu_base = None
+  if world == 1 and not args.no_gpu_baseline:
+    try:
+      gpu_base = stock_pytorch_leg(sd, opt.heads, B, H, W, dev, wt)
+    except Exception as e:                                    # noqa: BLE001
+      gpu_base = {'kind': 'port', 'error': repr(e)}
+    torch.cuda.empty_cache()
+
   cpu = None
   if not args.no_cpu_baseline and world == 1:       # rank 0 at N=1 only
     _use_host_threads()
@@ -621,7 +684,7 @@ def main():
           'decode_us': round(decode_ms * 1000, 1),
           'tracker_us': round(tracker_ms * 1000, 1) if tracker_ms is not None else None,
           'clocks': clocks, 'roofline': roofline, 'parity': parity, 'accurate_engine': accurate, 'latency': latency,
-          'cpu_baseline': cpu,
+          'gpu_baseline': gpu_base, 'cpu_baseline': cpu,
           'check': {'top_score_frame0': float(rec_last[0, 0, 0]), 'tracks_last_step': n_tracks_last}}
   _emit(line)
   if dist is not None:
