@@ -653,9 +653,9 @@ def main():
   if world == 1 and not args.no_gpu_baseline:
     try:
       gpu_base = stock_pytorch_leg(sd, opt.heads, B, H, W, dev, wt)
+      torch.cuda.empty_cache()
     except Exception as e:                                    # noqa: BLE001
       gpu_base = {'kind': 'port', 'error': repr(e)}
-    torch.cuda.empty_cache()
 
   cpu = None
   if not args.no_cpu_baseline and world == 1:       # rank 0 at N=1 only
