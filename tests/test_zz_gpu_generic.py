@@ -4,7 +4,7 @@ gen_generic).  With --head_conv 256 the plan that runs is launch for launch the 
 test_generic_arch_is_the_dla34_graph_under_other_names); the arch's own default head width is 64 (opts.py:295): the
 fused first head conv becomes 64 -> 64 x n_heads and the 1x1 heads read 64-channel slices of it.
 
-(File named to sort last: written after the round's GPU budget was spent)"""
+(Green on the B200: profiles/r02g_pytest_gpu_generic.log.)"""
 import os
 
 import numpy as np
