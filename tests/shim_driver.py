@@ -146,6 +146,35 @@ def main(ref_root, tmp):
   assert len(calls) == n_demo + 3
   ids = [sorted(r['tracking_id'] for r in evaluated[i]) for i in (1, 2, 3)]
   assert max(ids[2]) >= max(ids[0])                 # ids keep counting up through the video
+  # ---- the same again in the MOT public-detection protocol: --public_det --hungarian --load_results ------------------
+  # (test.py:64-70,90-108 -> meta['pre_dets'] / meta['cur_dets'] -> Tracker.init_track / Tracker.step(results, public_det))
+  pub = {}
+  for i in (1, 2, 3):
+    pts = [(20 + 40 * a, 20 + 40 * b) for a in range(4) for b in range(3)]           # 12 public detections on a grid
+    pub[str(i)] = [{'bbox': [x - 8., y - 8., x + 8., y + 8.], 'ct': [float(x), float(y)], 'score': 0.9, 'class': 1}
+                   for x, y in pts]
+  pub_path = os.path.join(tmp, 'public_dets.json')
+  json.dump(pub, open(pub_path, 'w'))
+  private = {k: list(v) for k, v in evaluated.items()}
+  evaluated.clear()
+  sys.argv = ['test.py', 'tracking', '--gpus', '0', '--pre_hm', '--track_thresh', '0.05', '--new_thresh', '0.05',
+              '--test_dataset', 'shimfake', '--exp_id', 'shimtest', '--not_set_cuda_env', '--public_det', '--hungarian',
+              '--load_results', pub_path]
+  opt = ref_opts.opts().parse()
+  opt.save_dir = os.path.join(tmp, 'exp')
+  opt.debug_dir = os.path.join(tmp, 'exp', 'debug')
+  ref_test.opt = opt
+  n_before = len(calls)
+  ref_test.prefetch_test(opt)
+  assert sorted(evaluated) == [1, 2, 3] and len(calls) == n_before + 3
+  seen = 12                                         # frame 1 starts from the 12 loaded pre_dets (ids 1..12)
+  for i in (1, 2, 3):
+    born = sorted(r['tracking_id'] for r in evaluated[i] if r['tracking_id'] > seen)
+    assert len(born) <= 12, (i, born)               # a track may only start on a public detection
+    assert born == list(range(seen + 1, seen + 1 + len(born)))
+    seen += len(born)
+  n_private = max(r['tracking_id'] for r in private[3])
+  assert seen - 12 < n_private, (seen, n_private)    # far fewer births than the private protocol on the same frames
   print('SHIM OK: demo.py 3 frames (%d video frames written), test.py 3 frames, %d stubbed process() calls'
         % (len(written), len(calls)))
 
