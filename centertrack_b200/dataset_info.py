@@ -26,11 +26,11 @@ dataset_factory = {
     'coco': DatasetInfo('coco', [512, 512], 80),
     'coco_hp': DatasetInfo('coco_hp', [512, 512], 1),
     'mot': DatasetInfo('mot', [544, 960], 1),
-    'crowdhuman': DatasetInfo('crowdhuman', [512, 512], 1),
+    'crowdhuman': DatasetInfo('crowdhuman', [512, 512], 1),  # the reference class leaves num_categories unset (crowdhuman.py:13: `num_classes`)
     'nuscenes': DatasetInfo('nuscenes', [448, 800], 10),
     'kitti': DatasetInfo('kitti', [384, 1280], 3),
     'kitti_tracking': DatasetInfo('kitti_tracking', [384, 1280], 3),
-    'custom': DatasetInfo('custom', [-1, -1], -1),
+    'custom': DatasetInfo('custom', [-1, -1], 1),           # custom_dataset.py:8-9: class-level defaults before --num_classes
 }
 
 

@@ -367,6 +367,31 @@ def gen_opts():
   with open(os.path.join(OUT, 'opts_cases.json'), 'w') as f:
     json.dump({'cases': OPT_CASES, 'fields': out}, f, indent=1)
   print('opts', len(out), 'cases')
+  # every flag of the reference's parser with its default (opts.py:11-254): the product parser must agree wherever it
+  # defines the same flag
+  defaults = {}
+  for a in opts().parser._actions:
+    if a.dest != 'help':
+      defaults[a.dest] = a.default
+  with open(os.path.join(OUT, 'opts_defaults.json'), 'w') as f:
+    json.dump(defaults, f, indent=1, sort_keys=True)
+  print('opts defaults', len(defaults), 'flags')
+
+
+def gen_dataset_info():
+  """The class attributes Detector.__init__ / opts read off the reference's dataset classes (detector.py:38-47,
+  opts.py:329-341): generic_dataset.py:21-52 and datasets/*.py."""
+  import json
+  from dataset.dataset_factory import dataset_factory
+  out = {}
+  for name, cls in sorted(dataset_factory.items()):
+    out[name] = {'default_resolution': list(cls.default_resolution), 'num_categories': None if cls.num_categories is None else int(cls.num_categories),
+                 'rest_focal_length': float(cls.rest_focal_length), 'num_joints': int(cls.num_joints),
+                 'flip_idx': [list(map(int, e)) for e in cls.flip_idx],
+                 'mean': np.asarray(cls.mean, np.float64).ravel().tolist(),
+                 'std': np.asarray(cls.std, np.float64).ravel().tolist()}
+  json.dump(out, open(os.path.join(OUT, 'dataset_info.json'), 'w'), indent=1, sort_keys=True)
+  print('dataset_info', sorted(out))
 
 
 def gen_host():
@@ -419,5 +444,6 @@ if __name__ == '__main__':
     gen_host()
   if 'opts' in which:
     gen_opts()
+    gen_dataset_info()
   if 'flip' in which:
     gen_flip()

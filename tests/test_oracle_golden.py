@@ -402,3 +402,32 @@ def test_unsupported_archs_raise_not_implemented():
     opt = make_opt('coco_tracking', ['--arch', arch])
     with pytest.raises(NotImplementedError):
       create_model(opt.arch, opt.heads, opt.head_conv, opt=opt)
+
+
+def test_dataset_constants_match_the_reference_classes(golden_dir):
+  """dataset_info.py against the class attributes of the reference's dataset classes (generic_dataset.py:21-52,
+  datasets/*.py; fixture written by oracle/gen_golden.py::gen_dataset_info).  `null` = the reference class leaves the
+  attribute unset (crowdhuman's num_categories), where the product may be more helpful."""
+  import json
+  from centertrack_b200.dataset_info import dataset_factory
+  g = json.load(open(os.path.join(golden_dir, 'dataset_info.json')))
+  assert sorted(g) == sorted(dataset_factory)
+  for name, ref in g.items():
+    d = dataset_factory[name]
+    for k in ('default_resolution', 'num_categories', 'rest_focal_length', 'num_joints', 'flip_idx'):
+      if ref[k] is not None:
+        got = getattr(d, k)
+        assert (list(got) if isinstance(got, (list, tuple)) else got) == ref[k], (name, k, got, ref[k])
+    assert np.allclose(np.ravel(d.mean), ref['mean'], atol=1e-7) and np.allclose(np.ravel(d.std), ref['std'], atol=1e-7)
+
+
+def test_product_flag_defaults_equal_the_reference_parser(golden_dir):
+  """Every flag the product parser shares with the reference's (opts.py:11-254, 134 flags dumped by
+  oracle/gen_golden.py::gen_opts into opts_defaults.json) has the same default; the only product-specific flags are
+  the --b200_* ones."""
+  import json
+  from centertrack_b200.opts import opts
+  ref = json.load(open(os.path.join(golden_dir, 'opts_defaults.json')))
+  mine = {a.dest: a.default for a in opts().parser._actions if a.dest != 'help'}
+  assert sorted(k for k in mine if k not in ref) == ['b200_device_pre', 'b200_precision']
+  assert {k: v for k, v in mine.items() if k in ref and ref[k] != v} == {}
