@@ -431,3 +431,21 @@ def test_product_flag_defaults_equal_the_reference_parser(golden_dir):
   mine = {a.dest: a.default for a in opts().parser._actions if a.dest != 'help'}
   assert sorted(k for k in mine if k not in ref) == ['b200_device_pre', 'b200_precision']
   assert {k: v for k, v in mine.items() if k in ref and ref[k] != v} == {}
+
+
+@pytest.mark.parametrize('extra', [['--hungarian'], ['--public_det'], ['--public_det', '--hungarian', '--max_age', '3'],
+                                   ['--max_age', '1']], ids=lambda e: '_'.join(x.strip('-') for x in e))
+def test_product_tracker_modes_equal_oracle_on_many_streams(extra):
+  """Beyond the golden's four streams: 24 more seeded crowded streams per mode, product tracker against the oracle
+  restatement (itself pinned to the reference by track_modes.npz) -- ids, age, active, class, order, boxes exact."""
+  import copy
+  from centertrack_b200.tracker import Tracker
+  for seed in range(10, 34):
+    opt = make_opt('coco_tracking', ['--track_thresh', '0.2', '--new_thresh', '0.3'] + extra)
+    prod = Tracker(opt)
+    orc = co.TrackerOracle(opt.new_thresh, opt.max_age, opt.hungarian, opt.public_det)
+    for f, (dets, pub) in enumerate(wt.synthetic_track_stream(seed, frames=5, crowd=30 + seed)):
+      if f == 0:
+        prod.init_track([]); orc.init_track([])
+      a, b = prod.step(copy.deepcopy(dets), pub), orc.step(copy.deepcopy(dets), pub)
+      assert prod.id_count == orc.id_count and np.array_equal(_track_rows(a), _track_rows(b)), (extra, seed, f)
