@@ -449,3 +449,66 @@ def test_product_tracker_modes_equal_oracle_on_many_streams(extra):
         prod.init_track([]); orc.init_track([])
       a, b = prod.step(copy.deepcopy(dets), pub), orc.step(copy.deepcopy(dets), pub)
       assert prod.id_count == orc.id_count and np.array_equal(_track_rows(a), _track_rows(b)), (extra, seed, f)
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_product_pre_hm_render_equals_oracle_on_random_tracks(seed):
+  """Detector._get_additional_inputs against the oracle restatement (pinned to the reference by host_pre.npz) on random
+  track sets: boxes partly / fully outside the frame, degenerate boxes, inactive and low-score tracks, every
+  resolution policy -- heat-maps and output-grid indices exact."""
+  from centertrack_b200.detector import Detector
+  from centertrack_b200.dataset_info import get_dataset
+  rng = np.random.RandomState(50 + seed)
+  name, extra, hw, _ = HOST_CASES[seed % len(HOST_CASES)]
+  opt = make_opt('coco_tracking', ['--pre_thresh', '0.3'] + extra)
+  opt.device = torch.device('cpu')
+  det = object.__new__(Detector)
+  ds = get_dataset(opt.dataset)
+  det.opt, det.rest_focal_length = opt, ds.rest_focal_length
+  det.mean = np.array(ds.mean, dtype=np.float32).reshape(1, 1, 3)
+  det.std = np.array(ds.std, dtype=np.float32).reshape(1, 1, 3)
+  h, w = int(rng.randint(60, 400)), int(rng.randint(60, 400))
+  image = rng.randint(0, 256, size=(h, w, 3)).astype(np.uint8)
+  _, meta = det.pre_process(image, 1.0, {})
+  tracks = []
+  for _ in range(int(rng.randint(0, 60))):
+    x0, y0 = rng.uniform(-0.3 * w, 1.1 * w), rng.uniform(-0.3 * h, 1.1 * h)
+    bw, bh = rng.choice([0.0, 1.0]) * rng.uniform(0, 0.6 * w), rng.uniform(0, 0.6 * h)
+    tracks.append({'score': float(rng.uniform(0.0, 1.0)), 'active': int(rng.randint(0, 3)),
+                   'bbox': [float(x0), float(y0), float(x0 + bw), float(y0 + bh)]})
+  hm, inds = det._get_additional_inputs(tracks, meta, with_hm=True)
+  ref_hm, ref_inds = co.render_pre_hm(tracks, meta['trans_input'], meta['trans_output'], meta['inp_width'],
+                                      meta['inp_height'], meta['out_width'], meta['out_height'], opt.pre_thresh)
+  assert np.array_equal(hm.numpy(), ref_hm) and np.array_equal(inds.numpy(), ref_inds)
+
+
+@pytest.mark.parametrize('ci', range(3))
+@pytest.mark.parametrize('seed', range(3))
+def test_product_post_process_equals_oracle_on_random_geometry(ci, seed):
+  """generic_post_process (post_process.py:21-91, ddd_utils.py:91-136) against the oracle restatement (pinned to the
+  reference by post_track.npz) for random source rectangles (c, s), image sizes and calibrations, on the coco / ddd /
+  pose head sets: every field of every kept detection to 1e-5 relative."""
+  from centertrack_b200.post_process import generic_post_process
+  cfg, kind, C, H, W = CASES[ci]
+  rng = np.random.RandomState(300 + 10 * ci + seed)
+  opt = make_opt(cfg, ['--track_thresh', '0.05', '--new_thresh', '0.05'])
+  inp = decode_inputs(kind, 1, C, H, W, 400 + 10 * ci + seed)
+  if 'dep' in inp:
+    inp['dep'] = (1. / (1. / (1 + np.exp(-inp['dep'] / 30 + 1)) + 1e-6) - 1.).astype(np.float32)
+  dets = {k: v for k, v in co.generic_decode(inp, 100).items() if not k.startswith('_')}
+  height, width = int(rng.randint(200, 900)), int(rng.randint(200, 1400))
+  c = np.array([width * rng.uniform(0.3, 0.7), height * rng.uniform(0.3, 0.7)], dtype=np.float32)
+  s = float(max(height, width) * rng.uniform(0.7, 1.4))
+  f = float(rng.uniform(500, 1500))
+  calib = np.array([[f, 0, width / 2, rng.uniform(-50, 50)], [0, f, height / 2, rng.uniform(-5, 5)],
+                    [0, 0, 1, rng.uniform(-0.01, 0.01)]], dtype=np.float32)
+  got = generic_post_process(opt, dets, [c], [s], H, W, opt.num_classes, [calib], height, width)[0]
+  ref = co.generic_post_process(dets, [c], [s], H, W, opt.out_thresh, [calib])[0]
+  got = [r for r in got if r['score'] > opt.out_thresh]
+  ref = [r for r in ref if r['score'] > opt.out_thresh]
+  assert len(got) == len(ref) > 0
+  for a, b in zip(got, ref):
+    assert set(a) == set(b)
+    for k in a:
+      x, y = np.asarray(a[k], np.float64), np.asarray(b[k], np.float64)
+      assert np.allclose(x, y, rtol=1e-5, atol=1e-4), (k, x, y)
